@@ -1,0 +1,162 @@
+"""Oracle (TEST INFRASTRUCTURE): Hi-C contact list -> window adjacency, on the CPU.
+
+Restates `data/7create_graph_new.py` of the reference twice:
+
+* `build_adjacency_loops`  -- record-at-a-time Python following the reference's
+  control flow (dict keyed by `(bin1, bin2)`, stable `sorted(..., reverse=True)`,
+  first `K` items, symmetric fill) -- for small cases;
+* `build_adjacency_numpy`  -- the same contract as array operations -- for sizes a
+  Python loop cannot finish in seconds.
+
+and `utils/util_methods.py` `process_graph('hic')` + `normalize` +
+`sparse_mx_to_torch_sparse_tensor` as `normalize_hic`.
+
+Both are pinned against the live reference by `tests/golden/make_golden.py`
+(adversarial input: heavy value ties, duplicate keys, reversed `(b, a)` keys, NaN / 0
+norm entries, diagonal and non-window rows).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def clean_norm_vector(norm: np.ndarray) -> np.ndarray:
+    """`get_normalization_values` (data/7create_graph_new.py:51-65): NaN -> +inf, 0.0 -> +inf."""
+    out = np.array(norm, dtype=np.float64, copy=True)
+    out[np.isnan(out)] = np.inf
+    out[out == 0.0] = np.inf
+    return out
+
+
+def _pairs_to_csr(n: int, pairs_i: np.ndarray, pairs_j: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """`create_adj_mat` (data/7create_graph_new.py:108-120) without the dense N x N matrix:
+    adj[i,j] = adj[j,i] = 1, then CSR (sorted columns, duplicates collapsed)."""
+    r = np.concatenate([pairs_i, pairs_j]).astype(np.int64)
+    c = np.concatenate([pairs_j, pairs_i]).astype(np.int64)
+    key = np.unique(r * np.int64(n) + c)
+    rows = key // n
+    cols = key % n
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(indptr, rows + 1, 1)
+    indptr = np.cumsum(indptr)
+    return indptr.astype(np.int32), cols.astype(np.int32)
+
+
+def build_adjacency_loops(window_starts, bin1, bin2, val, norm: Optional[np.ndarray],
+                          resolution_kb: int, hic_edges: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Record-at-a-time restatement; returns CSR `(indptr int32 [N+1], indices int32 [nnz])`.
+
+    window set / rank         data/7create_graph_new.py:24-44
+    contact filter + norm     :78-86     (norm is None  <=>  args.norm == '')
+    early exit                :88-89
+    stable top-K              :93-104
+    symmetric fill -> CSR     :108-120
+    """
+    starts = sorted(set(int(s) for s in window_starts))
+    rank = {s: t for t, s in enumerate(starts)}
+    k_pairs = int(hic_edges / 2.0)
+    nv = None if norm is None else clean_norm_vector(norm).tolist()
+    step = 1000 * int(resolution_kb)
+
+    table = {}          # insertion-ordered: position = first insert, value = last assignment
+    accepted = 0
+    for a, b, v in zip(np.asarray(bin1).tolist(), np.asarray(bin2).tolist(), np.asarray(val).tolist()):
+        if a == b or a not in rank or b not in rank:
+            continue
+        accepted += 1
+        if nv is not None:
+            v = v / (nv[int(a / step)] * nv[int(b / step)])
+        table[(a, b)] = v
+        if nv is None and accepted == k_pairs:
+            break
+
+    ranked = sorted(table.items(), key=lambda kv: kv[1], reverse=True)   # stable
+    chosen = ranked[:k_pairs] if k_pairs > 0 else ranked[:0]
+    # the reference's loop `idx += 1 ... if idx == total_edges: break` keeps >= 1 item when
+    # K == 0 and the dict is non-empty (it never hits idx == 0): honour that corner.
+    if k_pairs == 0 and ranked:
+        chosen = ranked
+    pi = np.array([rank[k[0]] for k, _ in chosen], dtype=np.int64)
+    pj = np.array([rank[k[1]] for k, _ in chosen], dtype=np.int64)
+    return _pairs_to_csr(len(starts), pi, pj)
+
+
+def build_adjacency_numpy(window_starts, bin1, bin2, val, norm: Optional[np.ndarray],
+                          resolution_kb: int, hic_edges: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Array restatement of the same contract."""
+    starts = np.unique(np.asarray(window_starts, dtype=np.int64))
+    n = starts.shape[0]
+    b1 = np.asarray(bin1, dtype=np.int64)
+    b2 = np.asarray(bin2, dtype=np.int64)
+    v = np.asarray(val, dtype=np.float64)
+    k_pairs = int(hic_edges / 2.0)
+
+    p1 = np.searchsorted(starts, b1)
+    p2 = np.searchsorted(starts, b2)
+    p1c = np.minimum(p1, n - 1)
+    p2c = np.minimum(p2, n - 1)
+    ok = (b1 != b2) & (starts[p1c] == b1) & (starts[p2c] == b2)
+    i, j, v = p1c[ok], p2c[ok], v[ok]
+    b1, b2 = b1[ok], b2[ok]
+
+    if norm is not None:
+        nv = clean_norm_vector(norm)
+        step = 1000 * int(resolution_kb)
+        with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+            v = v / (nv[b1 // step] * nv[b2 // step])
+    else:
+        if k_pairs > 0:                                       # first K accepted rows (:88-89)
+            i, j, v = i[:k_pairs], j[:k_pairs], v[:k_pairs]
+
+    key = i * np.int64(n) + j
+    order = np.argsort(key, kind="stable")                    # groups; file order inside a group
+    ks = key[order]
+    new_group = np.ones(ks.shape[0], dtype=bool)
+    new_group[1:] = ks[1:] != ks[:-1]
+    first_of_group = np.flatnonzero(new_group)
+    last_of_group = np.append(first_of_group[1:], ks.shape[0]) - 1
+    pos = order[first_of_group]                               # dict position = first insert
+    value = v[order[last_of_group]]                           # dict value    = last assignment
+    ukey = ks[first_of_group]
+
+    by_pos = np.argsort(pos, kind="stable")                   # dict iteration order
+    ukey, value = ukey[by_pos], value[by_pos]
+    ranked = np.argsort(-value, kind="stable")                # stable descending
+    take = ranked[:k_pairs] if k_pairs > 0 else ranked
+    sel = ukey[take]
+    return _pairs_to_csr(n, sel // n, sel % n)
+
+
+def normalize_hic(indptr, indices, n: Optional[int] = None):
+    """`process_graph('hic', ...)` (utils/util_methods.py:152-165,177-178).
+
+    Input: CSR pattern of the pickled binary adjacency (zero diagonal not required).
+    Output: `(rows int64, cols int64, vals float32)` of `D^-1 * bin(A + I)` in row-major,
+    ascending-column COO order -- the index/value arrays of the torch sparse tensor the
+    reference hands to `ChromeGCN.forward`.
+    """
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    n = indptr.shape[0] - 1 if n is None else n
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    key = np.unique(np.concatenate([rows * n + indices, np.arange(n, dtype=np.int64) * (n + 1)]))
+    r, c = key // n, key % n
+    deg = np.bincount(r, minlength=n).astype(np.float64)
+    vals = (1.0 / deg)[r].astype(np.float32)                  # float64 divide, then float32 cast
+    return r, c, vals
+
+
+def pattern_with_selfloops(indptr, indices):
+    """CSR pattern of `bin(A + I)` (int32 rowptr / colidx) -- what the CUDA path keeps on device."""
+    r, c, _ = normalize_hic(indptr, indices)
+    n = np.asarray(indptr).shape[0] - 1
+    rp = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(rp, r + 1, 1)
+    return np.cumsum(rp).astype(np.int32), c.astype(np.int32)
+
+
+def isnan(x: float) -> bool:
+    return math.isnan(x)

@@ -1,0 +1,180 @@
+"""Oracle (TEST INFRASTRUCTURE): the gated GCN chromosome model and its train step on the CPU.
+
+A plain-PyTorch (CPU) restatement of
+
+  models/SubLayers.py:8-52      GraphConvolution  (support = x W ; out = A_hat support + b)
+  models/ChromeModels.py:22-52  ChromeGCN         (tanh, per-row sigmoid gate, blend, ReLU,
+                                                  BatchNorm1d, dropout, Linear head)
+  finetune.py:29-53             one optimisation step per chromosome, both strands
+  utils/util_methods.py:14-19   SGD(momentum .9, wd 1e-6) / Adam(betas .9,.98)
+
+It uses the same torch primitives the reference uses (`torch.mm`, `torch.spmm` on an
+uncoalesced COO tensor, `F.dropout`, `nn.BatchNorm1d`, `F.binary_cross_entropy_with_logits`)
+so that, timed on the benchmark box's host cores, it stands in for "the reference's own
+PyTorch CPU GCN path" (`cpu_baseline.kind == "port"`).  State-dict keys and shapes are the
+reference's (`GC1.weight`, `GC1.bias`, `W1.weight`, ... `out.bias`), so checkpoints
+interchange.  Pinned against the live reference by tests/golden/make_golden.py.
+
+The only extension: `dropout_masks` lets a test inject the exact keep-masks (already
+scaled by 1/(1-p)) the CUDA path drew, because two different RNGs cannot be compared
+bit-for-bit.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import adjacency as _adj
+
+
+class GraphConvolutionOracle(nn.Module):
+    """models/SubLayers.py:8-52 (xavier_normal_ gain 0.02, zero bias: :32-35)."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(in_features, out_features))
+        self.bias = nn.Parameter(torch.zeros(out_features))
+        nn.init.xavier_normal_(self.weight, gain=0.02)
+
+    def forward(self, x, adj):
+        support = torch.mm(x, self.weight)
+        out = torch.spmm(adj, support) if adj is not None else support
+        return out + self.bias
+
+
+class ChromeGCNOracle(nn.Module):
+    """models/ChromeModels.py:21-52.  `layers == 2` gives two layers, anything else one
+    (reference quirk F7); the `gate` argument is accepted and ignored (F6)."""
+
+    def __init__(self, nfeat: int, nhid: int, nclass: int, dropout: float, gate=True, layers: int = 2):
+        super().__init__()
+        self.GC1 = GraphConvolutionOracle(nfeat, nhid)
+        self.W1 = nn.Linear(nfeat, 1)
+        if layers == 2:
+            self.GC2 = GraphConvolutionOracle(nhid, nfeat)
+            self.W2 = nn.Linear(nfeat, 1)
+        self.dropout = dropout
+        self.batch_norm = nn.BatchNorm1d(nfeat)
+        self.out = nn.Linear(nfeat, nclass)
+
+    def _drop(self, x, mask):
+        if mask is not None:
+            return x * mask
+        return F.dropout(x, self.dropout, training=self.training)
+
+    def forward(self, x_in, adj, deg=None, src_dict=None, return_gate=False,
+                dropout_masks: Optional[Sequence[Optional[torch.Tensor]]] = None):
+        m_mid, m_head = (dropout_masks if dropout_masks is not None else (None, None))
+        x = x_in
+        z = torch.tanh(self.GC1(x, adj))
+        g = torch.sigmoid(self.W1(z))
+        x = (1 - g) * x + g * z
+        g2 = None
+        if hasattr(self, "GC2"):
+            x = self._drop(x, m_mid)
+            z2 = torch.tanh(self.GC2(x, adj))
+            g2 = torch.sigmoid(self.W2(z2))
+            x = (1 - g2) * x + g2 * z2
+        x = F.relu(x)
+        x = self.batch_norm(x)
+        x = self._drop(x, m_head)
+        out = self.out(x)
+        return x_in, out, (g, g2), None
+
+
+def coo_adjacency(indptr, indices, dtype=torch.float32) -> torch.Tensor:
+    """The torch sparse COO tensor `process_graph('hic', ...)` returns
+    (utils/util_methods.py:120-135,177-178): int64 indices, fp32 values, not coalesced."""
+    r, c, v = _adj.normalize_hic(indptr, indices)
+    n = np.asarray(indptr).shape[0] - 1
+    idx = torch.from_numpy(np.vstack((r, c)).astype(np.int64))
+    val = torch.from_numpy(v).to(dtype)
+    return torch.sparse_coo_tensor(idx, val, (n, n), check_invariants=False)
+
+
+def make_optimizer(model: nn.Module, optim: str, lr: float):
+    """utils/util_methods.py:14-19."""
+    if optim == "adam":
+        return torch.optim.Adam(model.parameters(), betas=(0.9, 0.98), lr=lr)
+    if optim == "sgd":
+        return torch.optim.SGD(model.parameters(), lr=lr, weight_decay=1e-6, momentum=0.9)
+    raise ValueError(optim)
+
+
+def chromosome_step(model: ChromeGCNOracle, x_f, x_r, targets, adj, optimizer=None, train: bool = True,
+                    masks_f=None, masks_r=None, input_grads: bool = False):
+    """One iteration of the chromosome loop, finetune.py:30-53: both strands through the same
+    adjacency, mean of the two logit sets, BCE-with-logits (mean over N x nclass), backward,
+    optimiser step.  Returns `(loss float, probs [N, nclass], pred logits)`."""
+    if input_grads:
+        x_f = x_f.detach().requires_grad_(True)
+        x_r = x_r.detach().requires_grad_(True)
+    if train and optimizer is not None:
+        optimizer.zero_grad()
+    _, pred_f, gates_f, _ = model(x_f, adj, None, dropout_masks=masks_f)
+    _, pred_r, gates_r, _ = model(x_r, adj, None, dropout_masks=masks_r)
+    pred = (pred_f + pred_r) / 2
+    loss = F.binary_cross_entropy_with_logits(pred, targets.to(pred.dtype))
+    if train:
+        loss.backward()
+        if optimizer is not None:
+            optimizer.step()
+    extras = {"gates_f": gates_f, "gates_r": gates_r, "x_f": x_f, "x_r": x_r}
+    return float(loss.item()), torch.sigmoid(pred).detach(), pred.detach(), extras
+
+
+def finetune_epoch(model: ChromeGCNOracle, chrom_feature_dict: Dict[str, Dict[str, torch.Tensor]],
+                   graphs: Dict[str, Tuple[np.ndarray, np.ndarray]], optimizer, split: str = "train"):
+    """finetune.py:9-67 on the CPU: `graphs[chrom] = (indptr, indices)` of the pickled binary
+    adjacency; the D^-1(A+I) COO tensor is rebuilt per chromosome per epoch like the reference
+    does (`finetune.py:36`).  Returns `(all_preds, all_targets, total_loss)`."""
+    train = split == "train"
+    model.train(train)
+    preds, targs, total = [], [], 0.0
+    for chrom, feats in chrom_feature_dict.items():
+        adj = coo_adjacency(*graphs[chrom])
+        if train:
+            loss, prob, _, _ = chromosome_step(model, feats["forward"], feats["backward"], feats["target"],
+                                               adj, optimizer, True, input_grads=True)
+        else:
+            with torch.no_grad():
+                loss, prob, _, _ = chromosome_step(model, feats["forward"], feats["backward"],
+                                                   feats["target"], adj, None, False)
+        total += loss
+        preds.append(prob)
+        targs.append(feats["target"])
+    return torch.cat(preds, 0), torch.cat(targs, 0), total
+
+
+def stress_init_(model: nn.Module, seed: int = 7):
+    """A second, harsher weight setting (xavier gain 1.0, N(0,0.1) biases, non-trivial BN affine)
+    so tanh / sigmoid / BN leave their linear regime in parity tests."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("GC1.weight") or name.endswith("GC2.weight"):
+                fan = p.shape[0] + p.shape[1]
+                p.copy_(torch.randn(p.shape, generator=g) * (2.0 / fan) ** 0.5)
+            elif name == "batch_norm.weight":
+                p.copy_(1.0 + 0.2 * torch.randn(p.shape, generator=g))
+            elif name.endswith("bias"):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+            elif name in ("W1.weight", "W2.weight"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+            elif name == "out.weight":
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    return model
+
+
+def max_rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    """The tolerance metric of every fp parity test: max|a-b| / max|b| (max-norm relative)."""
+    a = a.detach().double()
+    b = b.detach().double()
+    denom = float(b.abs().max())
+    if denom == 0.0:
+        return float((a - b).abs().max())
+    return float((a - b).abs().max()) / denom

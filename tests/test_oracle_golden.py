@@ -1,0 +1,116 @@
+"""CPU: the oracle restatement against the golden vectors minted from the live reference
+(tests/golden/make_golden.py).  Integer work bit-exact; fp32 model within 2e-6 max-rel
+(thread-count dependent summation order in torch's CPU kernels is the only slack)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import adjacency as oadj
+from oracle import gcn as ogcn
+
+CHROMS = ["chr1", "chr2", "chr3", "chr22"]
+
+
+@pytest.mark.parametrize("fname", sorted(os.path.basename(p) for p in glob.glob(
+    os.path.join(os.path.dirname(__file__), "golden", "adjacency_*.npz"))))
+@pytest.mark.parametrize("impl", ["loops", "numpy"])
+def test_adjacency_bit_exact(golden_dir, fname, impl):
+    z = np.load(os.path.join(golden_dir, fname))
+    fn = oadj.build_adjacency_loops if impl == "loops" else oadj.build_adjacency_numpy
+    use_norm = str(z["norm_name"]) != ""
+    for c in CHROMS:
+        ip, ix = fn(z[c + "_windows"], z[c + "_bin1"], z[c + "_bin2"], z[c + "_val"],
+                    z[c + "_norm"] if use_norm else None, 1, int(z["hic_edges"]))
+        assert ip.dtype == np.int32 and ix.dtype == np.int32
+        assert np.array_equal(ip, z[c + "_indptr"]), (fname, c)
+        assert np.array_equal(ix, z[c + "_indices"]), (fname, c)
+        # structural properties of the reference's output
+        n = ip.shape[0] - 1
+        rows = np.repeat(np.arange(n), np.diff(ip))
+        assert not np.any(rows == ix)                                    # no diagonal
+        key = set(zip(rows.tolist(), ix.tolist()))
+        assert all((b, a) in key for a, b in key)                        # symmetric
+        assert len(key) <= 2 * max(int(int(z["hic_edges"]) / 2.0), 0) or int(z["hic_edges"]) < 2
+
+
+def test_process_graph_bit_exact(golden_dir):
+    z = np.load(os.path.join(golden_dir, "process_graph.npz"))
+    for c in CHROMS:
+        r, cc, v = oadj.normalize_hic(z[c + "_indptr"], z[c + "_indices"])
+        assert np.array_equal(r, z[c + "_coo_rows"])
+        assert np.array_equal(cc, z[c + "_coo_cols"])
+        assert v.dtype == np.float32 and np.array_equal(v, z[c + "_coo_vals"])
+        rp, ci = oadj.pattern_with_selfloops(z[c + "_indptr"], z[c + "_indices"])
+        assert rp[-1] == r.shape[0] and np.array_equal(ci, cc.astype(np.int32))
+
+
+def test_inverse_degree_is_correctly_rounded_fp32():
+    """float32(1.0 / float64(deg)) == 1.0f / float32(deg): the GPU computes the latter."""
+    deg = np.arange(1, 300001)
+    a = (1.0 / deg.astype(np.float64)).astype(np.float32)
+    b = (np.float32(1.0) / deg.astype(np.float32)).astype(np.float32)
+    assert np.array_equal(a, b)
+
+
+def _load_model(z, layers, dtype=torch.float32):
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0.")}
+    nclass = sd["out.weight"].shape[0]
+    m = ogcn.ChromeGCNOracle(128, 128, nclass, 0.0, True, layers)
+    m.load_state_dict(sd)
+    return m.to(dtype)
+
+
+@pytest.mark.parametrize("tag", ["l2_ref", "l2_stress", "l1_stress"])
+def test_model_matches_reference(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, "model_%s.npz" % tag))
+    layers = int(z["layers"])
+    x_f, x_r, tgt = (torch.from_numpy(z[k]) for k in ("x_f", "x_r", "target"))
+    adj = ogcn.coo_adjacency(z["indptr"], z["indices"])
+    tol = 2e-6
+    m = _load_model(z, layers)
+    m.eval()
+    with torch.no_grad():
+        _, out, (g1, g2), _ = m(x_f, adj)
+    assert ogcn.max_rel(out, torch.from_numpy(z["f32.eval.out_f"])) <= tol
+    assert ogcn.max_rel(g1, torch.from_numpy(z["f32.eval.g1_f"])) <= tol
+    m.train()
+    loss, prob, pred, ex = ogcn.chromosome_step(m, x_f, x_r, tgt, adj, None, True, input_grads=True)
+    assert abs(loss - float(z["f32.train.loss"])) <= tol * abs(float(z["f32.train.loss"]))
+    assert ogcn.max_rel(pred, torch.from_numpy(z["f32.train.pred"])) <= tol
+    # Gradients that are sums of signed terms over N rows (biases above all) cancel: the fp32
+    # reference itself is only ~1e-5 .. 2e-3 away from the fp64 reference there, and moves by that
+    # much with the CPU thread count.  Rule used everywhere in this repo: error against the fp64
+    # golden <= max(1e-5, 3 x the fp32 reference's own error against fp64).
+    for k, p in m.named_parameters():
+        ref64 = torch.from_numpy(z["f64.grad." + k])
+        own = ogcn.max_rel(torch.from_numpy(z["f32.grad." + k]), ref64)
+        assert ogcn.max_rel(p.grad, ref64) <= max(1e-5, 3 * own), k
+    assert ogcn.max_rel(ex["x_f"].grad, torch.from_numpy(z["f32.train.xgrad_f"])) <= 5e-6
+    assert ogcn.max_rel(m.batch_norm.running_mean, torch.from_numpy(z["f32.after.batch_norm.running_mean"])) <= tol
+    assert ogcn.max_rel(m.batch_norm.running_var, torch.from_numpy(z["f32.after.batch_norm.running_var"])) <= tol
+    assert int(m.batch_norm.num_batches_tracked) == int(z["f32.after.batch_norm.num_batches_tracked"]) == 2
+    # fp32 reference itself sits within ~1e-6 of the fp64 reference: the 1e-5 budget is real
+    assert ogcn.max_rel(torch.from_numpy(z["f32.train.pred"]), torch.from_numpy(z["f64.train.pred"])) <= 5e-6
+
+
+def test_finetune_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "finetune.npz"))
+    nclass = int(z["nclass"])
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0.")}
+    m = ogcn.ChromeGCNOracle(128, 128, nclass, 0.0, True, 2)
+    m.load_state_dict(sd)
+    opt = ogcn.make_optimizer(m, "sgd", 0.25)
+    feats = lambda cs: {c: {k: torch.from_numpy(z["%s.%s" % (c, k)]) for k in ("forward", "backward", "target")} for c in cs}
+    graphs = {c: (z[c + ".indptr"], z[c + ".indices"]) for c in ("chr1", "chr2", "chr3")}
+    for epoch in (1, 2, 3):
+        p, t, l = ogcn.finetune_epoch(m, feats(["chr1", "chr2"]), graphs, opt, "train")
+        pv, tv, lv = ogcn.finetune_epoch(m, feats(["chr3"]), graphs, opt, "valid")
+        assert abs(l - float(z["epoch%d.train_loss" % epoch])) <= 1e-5 * abs(l)
+        assert abs(lv - float(z["epoch%d.valid_loss" % epoch])) <= 1e-5 * abs(lv)
+        assert ogcn.max_rel(p, torch.from_numpy(z["epoch%d.train_preds" % epoch])) <= 1e-5
+        assert ogcn.max_rel(pv, torch.from_numpy(z["epoch%d.valid_preds" % epoch])) <= 1e-5
+    for k, v in m.state_dict().items():
+        assert ogcn.max_rel(v.float(), torch.from_numpy(z["sd3." + k]).float()) <= 2e-5, k
