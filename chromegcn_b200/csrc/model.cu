@@ -1,0 +1,382 @@
+// ChromeGCN.forward / its autograd / the finetune train step, as sequences of the kernels in
+// spmm.cu, gemm_*.cu and rowwise.cu on one stream (models/ChromeModels.py:34-52,
+// finetune.py:39-53).  Also the library-level entry points (version, errors, device info).
+//
+// Per layer the reference computes  A_hat (x W) + b ; this path computes (A_hat x) W + b
+// (same value up to fp32 rounding) because it makes
+//   d loss / d W = (A_hat x)^T (d loss / d y)
+// SpMM-free and lets the first layer skip its backward SpMM when nobody needs d loss / d x_in.
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+#include "rowwise_args.cuh"
+
+namespace cgcn {
+
+// ---- declarations of the launchers defined in the other translation units
+int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int scale_mode, const float* residual,
+                cudaStream_t stream);
+int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
+                       int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                       cudaStream_t stream);
+int gemm_gram_ffma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
+                   int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t gram_workspace_bytes(int64_t m);
+int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
+                     int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
+                 int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+bool tc_rowpanel_supported(int64_t lda, int64_t ldc, int n, int k, const void* A, const void* C);
+bool tc_gram_supported(int64_t lda, int64_t ldb, int ka, int nb, const void* A, const void* B);
+size_t tc_workspace_bytes();
+
+int rowwise_max_grid();
+int bce_grid();
+int bce_launch(const float* out, const float* target, int n, int C, int S, float* probs, float* loss_sum,
+               float* out_grad, float* partial, cudaStream_t stream);
+int colsum_launch(const float* X, int64_t rows, int cols, float* dst, float* partial, cudaStream_t stream);
+int bn_finalize_launch(const float* partial, int parts, int n, int S, int D, float eps, float momentum, int training,
+                       float* running_mean, float* running_var, int64_t* nbt, float* mean_out, float* rstd_out,
+                       cudaStream_t stream);
+int bn_bwd_finalize_launch(const float* partial, int parts, int n, int S, int D, int training, float* c1, float* c2,
+                           float* dgamma, float* dbeta, cudaStream_t stream);
+
+// ---- error string / counters
+static thread_local char tls_error[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tls_error, sizeof(tls_error), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
+
+// ---- dense dispatch
+int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
+                           int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                           int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const bool tc_ok = tc_rowpanel_supported(lda, ldc, n, k, A, C) && ws != nullptr && ws_bytes >= tc_workspace_bytes();
+  if (impl == 2 && !tc_ok) {
+    set_error("cgcn_gemm_rowpanel: tcgen05 path needs n = k = 128, 16-byte aligned rows and a workspace");
+    return CGCN_ERR_INVALID;
+  }
+  if (impl == 2 || (impl == 0 && tc_ok))
+    return gemm_rowpanel_tc(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_group, ws, ws_bytes,
+                            stream);
+  return gemm_rowpanel_ffma(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_group, stream);
+}
+
+int gemm_gram_dispatch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
+                       int ka, int nb, int accumulate, int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const bool tc_ok = tc_gram_supported(lda, ldb, ka, nb, A, B);
+  if (impl == 2 && !tc_ok) {
+    set_error("cgcn_gemm_gram: tcgen05 path needs ka = nb = 128 and 16-byte aligned rows");
+    return CGCN_ERR_INVALID;
+  }
+  if (impl == 2 || (impl == 0 && tc_ok))
+    return gemm_gram_tc(A, lda, B, ldb, C, ldc, m, ka, nb, accumulate, ws, ws_bytes, stream);
+  return gemm_gram_ffma(A, lda, B, ldb, C, ldc, m, ka, nb, accumulate, ws, ws_bytes, stream);
+}
+
+// ---- workspace layout (offsets in floats)
+struct WsLayout {
+  size_t ax[2], z[2], xo[2], hb;
+  size_t bn_mean, bn_rstd, bn_c1, bn_c2;
+  size_t dA, dB, dC;
+  size_t partial, partial_floats;
+  size_t gram, gram_bytes;
+  size_t tc, tc_bytes;
+  size_t total_floats;
+};
+
+static WsLayout make_layout(int n, int d, int nclass, int layers, int strands) {
+  (void)nclass;
+  WsLayout L{};
+  size_t off = 0;
+  auto take = [&](size_t floats) {
+    off = (off + 63) / 64 * 64;      // 256-byte alignment
+    const size_t r = off;
+    off += floats;
+    return r;
+  };
+  const size_t panel = static_cast<size_t>(n) * strands * d;
+  for (int l = 0; l < 2; ++l) {
+    const bool used = l < layers;
+    L.ax[l] = take(used ? panel : 0);
+    L.z[l] = take(used ? panel : 0);
+    L.xo[l] = take(used ? panel : 0);
+  }
+  L.hb = take(panel);
+  L.bn_mean = take(static_cast<size_t>(strands) * d);
+  L.bn_rstd = take(static_cast<size_t>(strands) * d);
+  L.bn_c1 = take(static_cast<size_t>(strands) * d);
+  L.bn_c2 = take(static_cast<size_t>(strands) * d);
+  L.dA = take(panel);
+  L.dB = take(panel);
+  L.dC = take(panel);
+  size_t per = static_cast<size_t>(2) * strands * d;
+  if (per < static_cast<size_t>(2 * d + 4)) per = 2 * d + 4;
+  if (per < 128) per = 128;
+  L.partial_floats = static_cast<size_t>(rowwise_max_grid()) * per;
+  L.partial = take(L.partial_floats);
+  L.gram_bytes = gram_workspace_bytes(static_cast<int64_t>(n) * strands);
+  L.gram = take((L.gram_bytes + 3) / 4);
+  L.tc_bytes = tc_workspace_bytes();
+  L.tc = take((L.tc_bytes + 3) / 4);
+  L.total_floats = (off + 63) / 64 * 64;
+  return L;
+}
+
+static int validate(const cgcn_model* m, bool backward) {
+  CGCN_REQUIRE(m != nullptr, "cgcn_model: null");
+  CGCN_REQUIRE(m->graph.n >= 1 && m->graph.rowptr && m->graph.colidx, "cgcn_model: bad graph");
+  CGCN_REQUIRE(m->d == 128, "cgcn_model: d=%d (the model path supports d = 128, the width main.py:62 fixes)", m->d);
+  CGCN_REQUIRE(m->nclass >= 1 && m->nclass <= 128, "cgcn_model: nclass=%d must be in [1,128]", m->nclass);
+  CGCN_REQUIRE(m->layers == 1 || m->layers == 2, "cgcn_model: layers=%d", m->layers);
+  CGCN_REQUIRE(m->strands == 1 || m->strands == 2, "cgcn_model: strands=%d", m->strands);
+  CGCN_REQUIRE(m->dropout_p >= 0.f && m->dropout_p < 1.f, "cgcn_model: dropout_p=%f", m->dropout_p);
+  CGCN_REQUIRE(m->x_in && m->out && m->gate[0] && (m->layers == 1 || m->gate[1]), "cgcn_model: null activation pointer");
+  CGCN_REQUIRE(m->bn_running_mean && m->bn_running_var, "cgcn_model: null BatchNorm running statistics");
+  for (int l = 0; l < m->layers; ++l)
+    CGCN_REQUIRE(m->params.gc_w[l] && m->params.gc_b[l] && m->params.gate_w[l] && m->params.gate_b[l],
+                 "cgcn_model: null layer-%d parameter", l);
+  CGCN_REQUIRE(m->params.bn_w && m->params.bn_b && m->params.out_w && m->params.out_b, "cgcn_model: null head parameter");
+  CGCN_REQUIRE(!(m->training && m->graph.n < 2), "cgcn_model: BatchNorm1d in training mode needs more than 1 row");
+  const size_t need = cgcn_model_workspace_bytes(m->graph.n, m->d, m->nclass, m->layers, m->strands);
+  if (m->workspace == nullptr || m->workspace_bytes < need) {
+    set_error("cgcn_model: workspace %zu < %zu bytes", m->workspace_bytes, need);
+    return CGCN_ERR_WORKSPACE;
+  }
+  if (backward) {
+    CGCN_REQUIRE(m->out_grad != nullptr, "cgcn_model_backward: null out_grad");
+    for (int l = 0; l < m->layers; ++l)
+      CGCN_REQUIRE(m->grads.gc_w[l] && m->grads.gc_b[l] && m->grads.gate_w[l] && m->grads.gate_b[l],
+                   "cgcn_model_backward: null layer-%d gradient", l);
+    CGCN_REQUIRE(m->grads.bn_w && m->grads.bn_b && m->grads.out_w && m->grads.out_b, "cgcn_model_backward: null head gradient");
+    CGCN_REQUIRE(!m->need_input_grad || m->x_in_grad, "cgcn_model_backward: need_input_grad without x_in_grad");
+  }
+  return CGCN_OK;
+}
+
+
+int gate_fwd_launch(const GateFwdArgs& a, int d, int S, bool stats, int* grid_out, cudaStream_t stream);
+int bn_apply_launch(const BnApplyArgs& a, cudaStream_t stream);
+int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, cudaStream_t stream);
+int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, float* db, float* dwg, float* dbg, cudaStream_t stream);
+
+static int model_forward(const cgcn_model* m) {
+  CGCN_TRY(validate(m, false));
+  cudaStream_t st = static_cast<cudaStream_t>(m->stream);
+  const int n = m->graph.n, d = m->d, S = m->strands, C = m->nclass, L = m->layers;
+  const int W = S * d;
+  const int64_t M = static_cast<int64_t>(n) * S;
+  const WsLayout lay = make_layout(n, d, C, L, S);
+  float* ws = m->workspace;
+  void* tcws = ws + lay.tc;
+
+  for (int l = 0; l < L; ++l) {
+    const float* xin = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
+    // ax = A_hat x                                   (torch.spmm, models/SubLayers.py:46)
+    CGCN_TRY(spmm_launch(&m->graph, xin, ws + lay.ax[l], W, 1, nullptr, st));
+    // y = ax W + b                                   (torch.mm + bias, models/SubLayers.py:43,50)
+    CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.ax[l], d, m->params.gc_w[l], 0, m->params.gc_b[l], ws + lay.z[l], d, M, d, d,
+                                    nullptr, 1, m->gemm_impl, tcws, lay.tc_bytes, st));
+    // z = tanh(y); g = sigmoid(W z); x' = (1-g) x + g z; dropout between the layers
+    //                                                (models/ChromeModels.py:38-42 / 44-46)
+    GateFwdArgs a{};
+    a.y = ws + lay.z[l];
+    a.x = xin;
+    a.wg = m->params.gate_w[l];
+    a.bg = m->params.gate_b[l];
+    a.z = ws + lay.z[l];
+    a.g = m->gate[l];
+    a.xo = ws + lay.xo[l];
+    a.stats_partial = ws + lay.partial;
+    a.n = n;
+    const bool last = (l == L - 1);
+    a.drop = make_dropout(m->dropout_p, m->seed, m->step, 0, m->training && !last);
+    int grid = 0;
+    CGCN_TRY(gate_fwd_launch(a, d, S, last && m->training, &grid, st));
+    if (last)
+      CGCN_TRY(bn_finalize_launch(ws + lay.partial, grid, n, S, d, m->bn_eps, m->bn_momentum, m->training,
+                                  m->bn_running_mean, m->bn_running_var, m->bn_num_batches_tracked, ws + lay.bn_mean,
+                                  ws + lay.bn_rstd, st));
+  }
+  // hb = dropout(BatchNorm(relu(x)))                 (models/ChromeModels.py:48-50)
+  BnApplyArgs b{};
+  b.h = ws + lay.xo[L - 1];
+  b.mean = ws + lay.bn_mean;
+  b.rstd = ws + lay.bn_rstd;
+  b.gamma = m->params.bn_w;
+  b.beta = m->params.bn_b;
+  b.hb = ws + lay.hb;
+  b.total4 = static_cast<int64_t>(n) * W / 4;
+  b.S = S;
+  b.D = d;
+  b.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training);
+  CGCN_TRY(bn_apply_launch(b, st));
+  // out = hb Wout^T + bout                           (models/ChromeModels.py:51)
+  CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.hb, d, m->params.out_w, 1, m->params.out_b, m->out, C, M, C, d, nullptr, 1,
+                                  m->gemm_impl, tcws, lay.tc_bytes, st));
+  return CGCN_OK;
+}
+
+static int model_backward(const cgcn_model* m) {
+  CGCN_TRY(validate(m, true));
+  cudaStream_t st = static_cast<cudaStream_t>(m->stream);
+  const int n = m->graph.n, d = m->d, S = m->strands, C = m->nclass, L = m->layers;
+  const int W = S * d;
+  const int64_t M = static_cast<int64_t>(n) * S;
+  const WsLayout lay = make_layout(n, d, C, L, S);
+  float* ws = m->workspace;
+  void* tcws = ws + lay.tc;
+  float* dA = ws + lay.dA;
+  float* dB = ws + lay.dB;
+  float* dC = ws + lay.dC;
+  void* gram_ws = ws + lay.gram;
+
+  // head: d out.weight = dout^T hb ; d out.bias = colsum(dout) ; d hb = dout Wout
+  CGCN_TRY(gemm_gram_dispatch(m->out_grad, C, ws + lay.hb, d, m->grads.out_w, d, M, C, d, 0, m->gemm_impl, gram_ws,
+                              lay.gram_bytes, st));
+  CGCN_TRY(colsum_launch(m->out_grad, M, C, m->grads.out_b, ws + lay.partial, st));
+  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, C, m->params.out_w, 0, nullptr, dA, d, M, d, C, nullptr, 1, m->gemm_impl,
+                                  tcws, lay.tc_bytes, st));
+  // BatchNorm backward sums
+  {
+    BnBwdReduceArgs r{};
+    r.dhb = dA;
+    r.h = ws + lay.xo[L - 1];
+    r.mean = ws + lay.bn_mean;
+    r.rstd = ws + lay.bn_rstd;
+    r.partial = ws + lay.partial;
+    r.n = n;
+    r.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training);
+    int grid = 0;
+    CGCN_TRY(bn_bwd_reduce_launch(r, d, S, &grid, st));
+    CGCN_TRY(bn_bwd_finalize_launch(ws + lay.partial, grid, n, S, d, m->training, ws + lay.bn_c1, ws + lay.bn_c2,
+                                    m->grads.bn_w, m->grads.bn_b, st));
+  }
+  // layers, last to first.  `src` holds the gradient entering the layer's gate stage.
+  const float* src = dA;
+  for (int l = L - 1; l >= 0; --l) {
+    const bool head = (l == L - 1);
+    const bool need_dx = (l > 0) || m->need_input_grad;
+    const float* xin = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
+    // the three scratch panels rotate: src is one of them, dy and dxd take the other two
+    float* dy = (src == dA) ? dB : dA;
+    float* dxd = (src == dC) ? ((dy == dA) ? dB : dA) : dC;
+    GateBwdArgs a{};
+    a.dsrc = src;
+    a.h = ws + lay.xo[l];
+    a.mean = ws + lay.bn_mean;
+    a.rstd = ws + lay.bn_rstd;
+    a.gamma = m->params.bn_w;
+    a.c1 = ws + lay.bn_c1;
+    a.c2 = ws + lay.bn_c2;
+    a.z = ws + lay.z[l];
+    a.x = xin;
+    a.g = m->gate[l];
+    a.wg = m->params.gate_w[l];
+    a.dy = dy;
+    a.dxd = need_dx ? dxd : nullptr;
+    a.partial = ws + lay.partial;
+    a.n = n;
+    a.drop = head ? make_dropout(m->dropout_p, m->seed, m->step, 1, m->training)
+                  : make_dropout(m->dropout_p, m->seed, m->step, 0, m->training);
+    CGCN_TRY(gate_bwd_launch(a, d, S, head, m->grads.gc_b[l], m->grads.gate_w[l], m->grads.gate_b[l], st));
+    // d W = (A_hat x)^T dy
+    CGCN_TRY(gemm_gram_dispatch(ws + lay.ax[l], d, dy, d, m->grads.gc_w[l], d, M, d, d, 0, m->gemm_impl, gram_ws,
+                                lay.gram_bytes, st));
+    if (!need_dx) break;
+    // t = D^-1 (dy W^T)  ->  the panel that held `src` ; then dx = dxd + P t
+    float* t = const_cast<float*>(src);
+    CGCN_TRY(gemm_rowpanel_dispatch(dy, d, m->params.gc_w[l], 1, nullptr, t, d, M, d, d, m->graph.rowptr, S, m->gemm_impl,
+                                    tcws, lay.tc_bytes, st));
+    float* dx = (l == 0) ? m->x_in_grad : dy;          // dy is dead after the two contractions above
+    CGCN_TRY(spmm_launch(&m->graph, t, dx, W, 0, dxd, st));
+    src = dx;
+  }
+  return CGCN_OK;
+}
+
+}  // namespace cgcn
+
+using namespace cgcn;
+
+extern "C" int cgcn_abi_version(void) { return CGCN_ABI_VERSION; }
+extern "C" const char* cgcn_last_error(void) { return tls_error; }
+extern "C" int64_t cgcn_launch_count(void) { return g_launches.load(); }
+
+extern "C" int cgcn_device_info(int32_t* sm, int32_t* major, int32_t* minor) {
+  int dev = 0;
+  CGCN_CUDA(cudaGetDevice(&dev));
+  int a = 0, b = 0, c = 0;
+  CGCN_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+  CGCN_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+  CGCN_CUDA(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm) *sm = a;
+  if (major) *major = b;
+  if (minor) *minor = c;
+  return CGCN_OK;
+}
+
+extern "C" size_t cgcn_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(cgcn_graph);
+    case 1: return sizeof(cgcn_params);
+    case 2: return sizeof(cgcn_model);
+    default: return 0;
+  }
+}
+
+extern "C" size_t cgcn_model_workspace_bytes(int32_t n, int32_t d, int32_t nclass, int32_t layers, int32_t strands) {
+  if (n < 1 || d < 1 || layers < 1 || layers > 2 || strands < 1 || strands > 2) return 0;
+  return make_layout(n, d, nclass, layers, strands).total_floats * sizeof(float);
+}
+
+extern "C" int cgcn_model_forward(const cgcn_model* m) { return model_forward(m); }
+extern "C" int cgcn_model_backward(const cgcn_model* m) { return model_backward(m); }
+
+extern "C" int cgcn_train_step(const cgcn_model* m, const float* target, float* probs, float* loss_sum_out,
+                               float* out_grad_scratch) {
+  CGCN_REQUIRE(m && target && loss_sum_out && out_grad_scratch, "cgcn_train_step: null argument");
+  CGCN_TRY(model_forward(m));
+  const WsLayout lay = make_layout(m->graph.n, m->d, m->nclass, m->layers, m->strands);
+  CGCN_TRY(bce_launch(m->out, target, m->graph.n, m->nclass, m->strands, probs, loss_sum_out, out_grad_scratch,
+                      m->workspace + lay.partial, static_cast<cudaStream_t>(m->stream)));
+  cgcn_model mb = *m;
+  mb.out_grad = out_grad_scratch;
+  return model_backward(&mb);
+}
+
+extern "C" int cgcn_gemm_rowpanel(const float* A, int64_t lda, const float* B, int32_t b_transposed, const float* bias,
+                                  float* C, int64_t ldc, int64_t m, int32_t n, int32_t k,
+                                  const int32_t* rowscale_rowptr, int32_t rowscale_group, int32_t gemm_impl,
+                                  void* workspace, size_t workspace_bytes, cgcn_stream_t stream) {
+  return gemm_rowpanel_dispatch(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_group,
+                                gemm_impl, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t cgcn_gemm_gram_workspace_bytes(int64_t m) { return gram_workspace_bytes(m); }
+
+extern "C" int cgcn_gemm_gram(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
+                              int32_t ka, int32_t nb, int32_t accumulate, int32_t gemm_impl, void* workspace,
+                              size_t workspace_bytes, cgcn_stream_t stream) {
+  return gemm_gram_dispatch(A, lda, B, ldb, C, ldc, m, ka, nb, accumulate, gemm_impl, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,676 @@
+// Row-wise (HBM-streaming) kernels of the gated GCN: everything in ChromeGCN.forward
+// (models/ChromeModels.py:34-52) and its autograd that is neither the SpMM nor a dense
+// contraction, fused so that each activation panel is read and written once per stage.
+//
+// Layout: panels are [n][S][D] fp32 (S strands interleaved, D = DV*128).  One warp owns one
+// window row at a time; lane l holds, per strand and per 128-column block v, the float4 at
+// column v*128 + 4*l, so every access is a coalesced 512 B request and the per-row gate
+// dot-product is one 5-step shuffle reduction.  Column reductions (bias / gate / BatchNorm
+// statistics and gradients) are accumulated in registers across the rows a warp visits,
+// combined per CTA in shared memory, written as per-CTA partials and summed in a fixed order
+// in fp64 by a small finalize kernel: deterministic, no fp32 atomics.
+#include "common.cuh"
+#include "rowwise_args.cuh"
+
+namespace cgcn {
+
+constexpr int RW_WARPS = 8;
+constexpr int RW_THREADS = RW_WARPS * 32;
+
+int rowwise_grid(int n) {
+  const int by_rows = (n + RW_WARPS - 1) / RW_WARPS;
+  const int cap = sm_count() * 8;
+  return by_rows < cap ? (by_rows > 0 ? by_rows : 1) : cap;
+}
+int rowwise_max_grid() { return sm_count() * 8; }
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ void add4(float4& a, float4 b) {
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
+}
+
+// Combine per-warp register accumulators (K floats per warp, laid out by `store`) into one
+// per-CTA partial row.  red: [RW_WARPS][K] floats of dynamic shared memory.
+__device__ __forceinline__ void block_combine(float* red, int K, float* __restrict__ dst) {
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < K; idx += RW_THREADS) {
+    float t = red[idx];
+#pragma unroll
+    for (int w = 1; w < RW_WARPS; ++w) t += red[w * K + idx];
+    dst[idx] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------- gate forward
+
+template <int DV, int S, bool STATS>
+__global__ void __launch_bounds__(RW_THREADS) gate_fwd_kernel(const GateFwdArgs a) {
+  constexpr int D = DV * 128;
+  constexpr int K = 2 * S * D;
+  extern __shared__ __align__(16) float red[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 wg[DV];
+#pragma unroll
+  for (int v = 0; v < DV; ++v) wg[v] = ldg4(a.wg + v * 128 + lane * 4);
+  const float bg = __ldg(a.bg);
+  float4 ssum[STATS ? S : 1][STATS ? DV : 1], ssq[STATS ? S : 1][STATS ? DV : 1];
+  if constexpr (STATS) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+      for (int v = 0; v < DV; ++v) ssum[s][v] = ssq[s][v] = f4_zero();
+  }
+  for (int row = blockIdx.x * RW_WARPS + warp; row < a.n; row += gridDim.x * RW_WARPS) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const size_t base = (static_cast<size_t>(row) * S + s) * D + lane * 4;
+      float4 z[DV];
+      float dot = 0.f;
+#pragma unroll
+      for (int v = 0; v < DV; ++v) {
+        const float4 y = ld4(a.y + base + v * 128);
+        z[v] = make_float4(tanhf(y.x), tanhf(y.y), tanhf(y.z), tanhf(y.w));
+        dot += dot4(z[v], wg[v]);
+      }
+      dot = warp_sum(dot);
+      const float g = sigmoidf_(dot + bg);
+      const float omg = 1.0f - g;
+      if (lane == 0) a.g[static_cast<size_t>(row) * S + s] = g;
+#pragma unroll
+      for (int v = 0; v < DV; ++v) {
+        const float4 x = ldg4(a.x + base + v * 128);
+        float4 h = make_float4(omg * x.x + g * z[v].x, omg * x.y + g * z[v].y, omg * x.z + g * z[v].z,
+                               omg * x.w + g * z[v].w);
+        if (a.drop.enabled) {
+          const float4 m = dropout_mult4(a.drop, (base + v * 128) >> 2);
+          h = make_float4(h.x * m.x, h.y * m.y, h.z * m.z, h.w * m.w);
+        }
+        st4(a.z + base + v * 128, z[v]);
+        st4(a.xo + base + v * 128, h);
+        if constexpr (STATS) {
+          const float4 r = make_float4(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f), fmaxf(h.z, 0.f), fmaxf(h.w, 0.f));
+          add4(ssum[s][v], r);
+          add4(ssq[s][v], make_float4(r.x * r.x, r.y * r.y, r.z * r.z, r.w * r.w));
+        }
+      }
+    }
+  }
+  if constexpr (STATS) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+      for (int v = 0; v < DV; ++v) {
+        st4(red + warp * K + (0 * S + s) * D + v * 128 + lane * 4, ssum[s][v]);
+        st4(red + warp * K + (1 * S + s) * D + v * 128 + lane * 4, ssq[s][v]);
+      }
+    block_combine(red, K, a.stats_partial + static_cast<size_t>(blockIdx.x) * K);
+  }
+}
+
+// BatchNorm1d statistics (models/ChromeModels.py:49): per strand call, batch mean / biased variance
+// over the n rows; running stats updated once per strand, in strand order, with the unbiased
+// variance (torch.nn.BatchNorm1d semantics).  Eval mode: running stats.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int parts, int n, int S, int D, float eps,
+                                   float momentum, int training, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int64_t* __restrict__ num_batches,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const int K = 2 * S * D;
+  if (!training) {
+    const float m = running_mean[c];
+    const float r = static_cast<float>(1.0 / sqrt(static_cast<double>(running_var[c]) + static_cast<double>(eps)));
+    for (int s = 0; s < S; ++s) {
+      mean_out[s * D + c] = m;
+      rstd_out[s * D + c] = r;
+    }
+    return;
+  }
+  float rm = running_mean[c], rv = running_var[c];
+  for (int s = 0; s < S; ++s) {
+    double sum = 0.0, sq = 0.0;
+    for (int q = 0; q < parts; ++q) {
+      sum += static_cast<double>(partial[static_cast<size_t>(q) * K + (0 * S + s) * D + c]);
+      sq += static_cast<double>(partial[static_cast<size_t>(q) * K + (1 * S + s) * D + c]);
+    }
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_out[s * D + c] = static_cast<float>(mean);
+    rstd_out[s * D + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const double unbiased = n > 1 ? var * n / (n - 1.0) : var;
+    rm = (1.0f - momentum) * rm + momentum * static_cast<float>(mean);
+    rv = (1.0f - momentum) * rv + momentum * static_cast<float>(unbiased);
+  }
+  running_mean[c] = rm;
+  running_var[c] = rv;
+  if (c == 0 && num_batches != nullptr) *num_batches += S;
+}
+
+// hb = dropout(gamma * (relu(h) - mean) * rstd + beta)      (models/ChromeModels.py:48-50)
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < a.total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = i * 4;
+    const int c = static_cast<int>(e % a.D);
+    const int s = static_cast<int>((e / a.D) % a.S);
+    const float4 h = ldg4(a.h + e);
+    const float4 mu = ldg4(a.mean + s * a.D + c), rs = ldg4(a.rstd + s * a.D + c);
+    const float4 ga = ldg4(a.gamma + c), be = ldg4(a.beta + c);
+    float4 o = make_float4((fmaxf(h.x, 0.f) - mu.x) * rs.x * ga.x + be.x, (fmaxf(h.y, 0.f) - mu.y) * rs.y * ga.y + be.y,
+                           (fmaxf(h.z, 0.f) - mu.z) * rs.z * ga.z + be.z, (fmaxf(h.w, 0.f) - mu.w) * rs.w * ga.w + be.w);
+    if (a.drop.enabled) {
+      const float4 m = dropout_mult4(a.drop, static_cast<uint64_t>(i));
+      o = make_float4(o.x * m.x, o.y * m.y, o.z * m.z, o.w * m.w);
+    }
+    st4(a.hb + e, o);
+  }
+}
+
+// ------------------------------------------------------------------------------ BN backward sums
+
+template <int DV, int S>
+__global__ void __launch_bounds__(RW_THREADS) bn_bwd_reduce_kernel(const BnBwdReduceArgs a) {
+  constexpr int D = DV * 128;
+  constexpr int K = 2 * S * D;
+  extern __shared__ __align__(16) float red[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 s1[S][DV], s2[S][DV];
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int v = 0; v < DV; ++v) s1[s][v] = s2[s][v] = f4_zero();
+  for (int row = blockIdx.x * RW_WARPS + warp; row < a.n; row += gridDim.x * RW_WARPS) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const size_t base = (static_cast<size_t>(row) * S + s) * D + lane * 4;
+#pragma unroll
+      for (int v = 0; v < DV; ++v) {
+        float4 g = ldg4(a.dhb + base + v * 128);
+        if (a.drop.enabled) {
+          const float4 m = dropout_mult4(a.drop, (base + v * 128) >> 2);
+          g = make_float4(g.x * m.x, g.y * m.y, g.z * m.z, g.w * m.w);
+        }
+        const float4 h = ldg4(a.h + base + v * 128);
+        const float4 mu = ldg4(a.mean + s * D + v * 128 + lane * 4), rs = ldg4(a.rstd + s * D + v * 128 + lane * 4);
+        const float4 xh = make_float4((fmaxf(h.x, 0.f) - mu.x) * rs.x, (fmaxf(h.y, 0.f) - mu.y) * rs.y,
+                                      (fmaxf(h.z, 0.f) - mu.z) * rs.z, (fmaxf(h.w, 0.f) - mu.w) * rs.w);
+        add4(s1[s][v], g);
+        add4(s2[s][v], make_float4(g.x * xh.x, g.y * xh.y, g.z * xh.z, g.w * xh.w));
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int v = 0; v < DV; ++v) {
+      st4(red + warp * K + (0 * S + s) * D + v * 128 + lane * 4, s1[s][v]);
+      st4(red + warp * K + (1 * S + s) * D + v * 128 + lane * 4, s2[s][v]);
+    }
+  block_combine(red, K, a.partial + static_cast<size_t>(blockIdx.x) * K);
+}
+
+// c1 = mean(dbn), c2 = mean(dbn * xhat) per strand (zero in eval mode: running stats are constants);
+// d gamma = sum_s sum dbn*xhat ; d beta = sum_s sum dbn.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int n, int S, int D, int training,
+                                       float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const int K = 2 * S * D;
+  double tg = 0.0, tb = 0.0;
+  for (int s = 0; s < S; ++s) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int q = 0; q < parts; ++q) {
+      a1 += static_cast<double>(partial[static_cast<size_t>(q) * K + (0 * S + s) * D + c]);
+      a2 += static_cast<double>(partial[static_cast<size_t>(q) * K + (1 * S + s) * D + c]);
+    }
+    c1[s * D + c] = training ? static_cast<float>(a1 / n) : 0.f;
+    c2[s * D + c] = training ? static_cast<float>(a2 / n) : 0.f;
+    tb += a1;
+    tg += a2;
+  }
+  dgamma[c] = static_cast<float>(tg);
+  dbeta[c] = static_cast<float>(tb);
+}
+
+// ------------------------------------------------------------------------------ gate backward
+
+template <int DV, int S, int HEAD>
+__global__ void __launch_bounds__(RW_THREADS) gate_bwd_kernel(const GateBwdArgs a) {
+  constexpr int D = DV * 128;
+  constexpr int K = 2 * D + 4;
+  extern __shared__ __align__(16) float red[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 wg[DV], db[DV], dwg[DV];
+  float dbg = 0.f;
+#pragma unroll
+  for (int v = 0; v < DV; ++v) {
+    wg[v] = ldg4(a.wg + v * 128 + lane * 4);
+    db[v] = dwg[v] = f4_zero();
+  }
+  for (int row = blockIdx.x * RW_WARPS + warp; row < a.n; row += gridDim.x * RW_WARPS) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const size_t base = (static_cast<size_t>(row) * S + s) * D + lane * 4;
+      float4 dh[DV], z[DV], x[DV];
+      float part = 0.f;
+#pragma unroll
+      for (int v = 0; v < DV; ++v) {
+        float4 d = ldg4(a.dsrc + base + v * 128);
+        if (a.drop.enabled) {
+          const float4 m = dropout_mult4(a.drop, (base + v * 128) >> 2);
+          d = make_float4(d.x * m.x, d.y * m.y, d.z * m.z, d.w * m.w);
+        }
+        if (HEAD) {
+          const int co = s * D + v * 128 + lane * 4;
+          const float4 h = ldg4(a.h + base + v * 128);
+          const float4 mu = ldg4(a.mean + co), rs = ldg4(a.rstd + co), k1 = ldg4(a.c1 + co), k2 = ldg4(a.c2 + co);
+          const float4 ga = ldg4(a.gamma + v * 128 + lane * 4);
+          float4 r;
+          r.x = h.x > 0.f ? ga.x * rs.x * (d.x - k1.x - (h.x - mu.x) * rs.x * k2.x) : 0.f;
+          r.y = h.y > 0.f ? ga.y * rs.y * (d.y - k1.y - (h.y - mu.y) * rs.y * k2.y) : 0.f;
+          r.z = h.z > 0.f ? ga.z * rs.z * (d.z - k1.z - (h.z - mu.z) * rs.z * k2.z) : 0.f;
+          r.w = h.w > 0.f ? ga.w * rs.w * (d.w - k1.w - (h.w - mu.w) * rs.w * k2.w) : 0.f;
+          d = r;
+        }
+        dh[v] = d;
+        z[v] = ldg4(a.z + base + v * 128);
+        x[v] = ldg4(a.x + base + v * 128);
+        part += d.x * (z[v].x - x[v].x) + d.y * (z[v].y - x[v].y) + d.z * (z[v].z - x[v].z) + d.w * (z[v].w - x[v].w);
+      }
+      part = warp_sum(part);
+      const float g = __ldg(a.g + static_cast<size_t>(row) * S + s);
+      const float dgp = part * g * (1.0f - g);
+      const float omg = 1.0f - g;
+#pragma unroll
+      for (int v = 0; v < DV; ++v) {
+        const float4 dz = make_float4(g * dh[v].x + dgp * wg[v].x, g * dh[v].y + dgp * wg[v].y,
+                                      g * dh[v].z + dgp * wg[v].z, g * dh[v].w + dgp * wg[v].w);
+        const float4 dy = make_float4(dz.x * (1.0f - z[v].x * z[v].x), dz.y * (1.0f - z[v].y * z[v].y),
+                                      dz.z * (1.0f - z[v].z * z[v].z), dz.w * (1.0f - z[v].w * z[v].w));
+        st4(a.dy + base + v * 128, dy);
+        if (a.dxd != nullptr)
+          st4(a.dxd + base + v * 128, make_float4(omg * dh[v].x, omg * dh[v].y, omg * dh[v].z, omg * dh[v].w));
+        add4(db[v], dy);
+        add4(dwg[v], make_float4(dgp * z[v].x, dgp * z[v].y, dgp * z[v].z, dgp * z[v].w));
+      }
+      dbg += dgp;                      // identical in every lane
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < DV; ++v) {
+    st4(red + warp * K + v * 128 + lane * 4, db[v]);
+    st4(red + warp * K + D + v * 128 + lane * 4, dwg[v]);
+  }
+  if (lane < 4) red[warp * K + 2 * D + lane] = (lane == 0) ? dbg : 0.f;
+  block_combine(red, K, a.partial + static_cast<size_t>(blockIdx.x) * K);
+}
+
+// out[k] = sum over parts of partial[part*stride + k], routed to up to three destinations
+struct ColFinalizeArgs {
+  const float* partial;
+  int parts, stride;
+  float* dst[3];
+  int begin[3], len[3];
+};
+
+__global__ void col_finalize_kernel(const ColFinalizeArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (a.dst[q] == nullptr || t >= a.len[q]) continue;
+    double s = 0.0;
+    for (int p = 0; p < a.parts; ++p) s += static_cast<double>(a.partial[static_cast<size_t>(p) * a.stride + a.begin[q] + t]);
+    a.dst[q][t] = static_cast<float>(s);
+  }
+}
+
+// ------------------------------------------------------------------------------ generic column sum
+// dst[c] = sum_r X[r][c], X [rows][cols] with arbitrary cols <= 128 (d out.bias = column sums of the
+// logit gradient).  One thread per column, 8 rows in flight.
+__global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols,
+                                                             int64_t rows_per_cta, float* __restrict__ partial) {
+  const int c = threadIdx.x;
+  const int64_t r0 = blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(r0 + rows_per_cta, rows);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < cols) {
+    int64_t r = r0;
+    for (; r + 8 <= r1; r += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += __ldg(X + (r + u) * cols + c);
+    }
+    for (; r < r1; ++r) acc[0] += __ldg(X + r * cols + c);
+  }
+  const float t = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  partial[static_cast<size_t>(blockIdx.x) * 128 + c] = (c < cols) ? t : 0.f;
+}
+
+// ------------------------------------------------------------------------------ BCE-with-logits
+struct BceArgs {
+  const float* out;    // [n][S][C]
+  const float* target; // [n][C]
+  float* probs;        // [n][C] or NULL
+  float* out_grad;     // [n][S][C] or NULL
+  float* partial;      // [grid]
+  int64_t total;       // n*C
+  int C, S;
+  float inv_count;     // 1 / (n*C)
+};
+
+__global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
+  __shared__ float wsum[8];
+  float local = 0.f;
+  const float inv_s = 1.0f / a.S;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < a.total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e / a.C;
+    const int c = static_cast<int>(e - r * a.C);
+    float p = 0.f;
+    for (int s = 0; s < a.S; ++s) p += __ldg(a.out + (r * a.S + s) * a.C + c);
+    p *= inv_s;                                               // (pred_f + pred_r) / 2, finetune.py:43
+    const float t = __ldg(a.target + e);
+    local += fmaxf(p, 0.f) - p * t + log1pf(expf(-fabsf(p)));  // F.binary_cross_entropy_with_logits, finetune.py:45
+    const float pr = sigmoidf_(p);
+    if (a.probs != nullptr) a.probs[e] = pr;                  // F.sigmoid(pred), finetune.py:52
+    if (a.out_grad != nullptr) {
+      const float gsc = (pr - t) * a.inv_count * inv_s;
+      for (int s = 0; s < a.S; ++s) a.out_grad[(r * a.S + s) * a.C + c] = gsc;
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    a.partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void bce_finalize_kernel(const float* __restrict__ partial, int parts, float inv_count, float* loss_sum) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int p = 0; p < parts; ++p) s += static_cast<double>(partial[p]);
+    *loss_sum += static_cast<float>(s * static_cast<double>(inv_count));
+  }
+}
+
+// ------------------------------------------------------------------------------ optimisers
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t count,
+                           float lr, float momentum, float wd, float gscale) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= count) return;
+  const float w = p[i];
+  float d = g[i] * gscale;
+  d = fmaf(wd, w, d);                       // grad.add(param, alpha=weight_decay)
+  const float b = momentum * buf[i] + d;    // buf.mul_(momentum).add_(grad)   (buf starts at 0 == first-step clone)
+  buf[i] = b;
+  p[i] = w - lr * b;                        // param.add_(buf, alpha=-lr)
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t count, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt, float gscale) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= count) return;
+  const float gr = g[i] * gscale;
+  const float mi = m[i] + (gr - m[i]) * (1.0f - b1);          // exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
+// ------------------------------------------------------------------------------ utilities
+__global__ void interleave_kernel(const float* s0, const float* s1, int S, int64_t n, int d4, float4* dst) {
+  const int64_t total = n * S * d4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % d4);
+    const int s = static_cast<int>((i / d4) % S);
+    const int64_t r = i / (static_cast<int64_t>(d4) * S);
+    const float* src = s == 0 ? s0 : s1;
+    dst[i] = __ldg(reinterpret_cast<const float4*>(src) + r * d4 + c);
+  }
+}
+
+__global__ void deinterleave_kernel(const float* src, int S, int64_t n, int w, float* d0, float* d1) {
+  const int64_t total = n * S * w;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % w);
+    const int s = static_cast<int>((i / w) % S);
+    const int64_t r = i / (static_cast<int64_t>(w) * S);
+    (s == 0 ? d0 : d1)[r * w + c] = __ldg(src + i);
+  }
+}
+
+__global__ void dropout_mask_kernel(float4* mask, int64_t total4, DropoutCfg cfg) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    mask[i] = cfg.enabled ? dropout_mult4(cfg, static_cast<uint64_t>(i)) : make_float4(1.f, 1.f, 1.f, 1.f);
+}
+
+// =============================================================================== host launchers
+static int flat_grid(int64_t work_items, int threads) {
+  int64_t b = (work_items + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+template <typename KernelT>
+static int ensure_smem(KernelT kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CGCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  return CGCN_OK;
+}
+
+#define DISPATCH_DV_S(DVV, SV, MACRO)                                                              \
+  do {                                                                                             \
+    if ((DVV) == 1 && (SV) == 1) { MACRO(1, 1); }                                                  \
+    else if ((DVV) == 1 && (SV) == 2) { MACRO(1, 2); }                                             \
+    else if ((DVV) == 2 && (SV) == 1) { MACRO(2, 1); }                                             \
+    else if ((DVV) == 2 && (SV) == 2) { MACRO(2, 2); }                                             \
+    else if ((DVV) == 4 && (SV) == 1) { MACRO(4, 1); }                                             \
+    else if ((DVV) == 4 && (SV) == 2) { MACRO(4, 2); }                                             \
+    else { set_error("unsupported d=%d strands=%d (d must be 128, 256 or 512; strands 1 or 2)", (DVV) * 128, (SV)); return CGCN_ERR_INVALID; } \
+  } while (0)
+
+int gate_fwd_launch(const GateFwdArgs& a, int d, int S, bool stats, int* grid_out, cudaStream_t stream) {
+  const int grid = rowwise_grid(a.n);
+  if (grid_out) *grid_out = grid;
+  const int dv = d / 128;
+  const size_t smem = stats ? static_cast<size_t>(RW_WARPS) * 2 * S * d * sizeof(float) : 0;
+#define GF(DVC, SC)                                                                          \
+  if (stats) {                                                                               \
+    CGCN_TRY(ensure_smem(gate_fwd_kernel<DVC, SC, true>, smem));                             \
+    gate_fwd_kernel<DVC, SC, true><<<grid, RW_THREADS, smem, stream>>>(a);                   \
+  } else {                                                                                   \
+    gate_fwd_kernel<DVC, SC, false><<<grid, RW_THREADS, 0, stream>>>(a);                     \
+  }
+  DISPATCH_DV_S(dv, S, GF);
+#undef GF
+  return check_launch("gate_fwd_kernel");
+}
+
+int bn_finalize_launch(const float* partial, int parts, int n, int S, int D, float eps, float momentum, int training,
+                       float* running_mean, float* running_var, int64_t* nbt, float* mean_out, float* rstd_out,
+                       cudaStream_t stream) {
+  bn_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, parts, n, S, D, eps, momentum, training, running_mean,
+                                                          running_var, nbt, mean_out, rstd_out);
+  return check_launch("bn_finalize_kernel");
+}
+
+int bn_apply_launch(const BnApplyArgs& a, cudaStream_t stream) {
+  bn_apply_kernel<<<flat_grid(a.total4, 256), 256, 0, stream>>>(a);
+  return check_launch("bn_apply_kernel");
+}
+
+int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, cudaStream_t stream) {
+  const int grid = rowwise_grid(a.n);
+  if (grid_out) *grid_out = grid;
+  const int dv = d / 128;
+  const size_t smem = static_cast<size_t>(RW_WARPS) * 2 * S * d * sizeof(float);
+#define BR(DVC, SC)                                                    \
+  CGCN_TRY(ensure_smem(bn_bwd_reduce_kernel<DVC, SC>, smem));          \
+  bn_bwd_reduce_kernel<DVC, SC><<<grid, RW_THREADS, smem, stream>>>(a);
+  DISPATCH_DV_S(dv, S, BR);
+#undef BR
+  return check_launch("bn_bwd_reduce_kernel");
+}
+
+int bn_bwd_finalize_launch(const float* partial, int parts, int n, int S, int D, int training, float* c1, float* c2,
+                           float* dgamma, float* dbeta, cudaStream_t stream) {
+  bn_bwd_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, parts, n, S, D, training, c1, c2, dgamma, dbeta);
+  return check_launch("bn_bwd_finalize_kernel");
+}
+
+int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, float* db, float* dwg, float* dbg,
+                    cudaStream_t stream) {
+  const int grid = rowwise_grid(a.n);
+  const int dv = d / 128;
+  const int K = 2 * d + 4;
+  const size_t smem = static_cast<size_t>(RW_WARPS) * K * sizeof(float);
+#define GBW(DVC, SC)                                                            \
+  if (head) {                                                                   \
+    CGCN_TRY(ensure_smem(gate_bwd_kernel<DVC, SC, 1>, smem));                   \
+    gate_bwd_kernel<DVC, SC, 1><<<grid, RW_THREADS, smem, stream>>>(a);         \
+  } else {                                                                      \
+    CGCN_TRY(ensure_smem(gate_bwd_kernel<DVC, SC, 0>, smem));                   \
+    gate_bwd_kernel<DVC, SC, 0><<<grid, RW_THREADS, smem, stream>>>(a);         \
+  }
+  DISPATCH_DV_S(dv, S, GBW);
+#undef GBW
+  CGCN_TRY(check_launch("gate_bwd_kernel"));
+  ColFinalizeArgs f{};
+  f.partial = a.partial;
+  f.parts = grid;
+  f.stride = K;
+  f.dst[0] = db;  f.begin[0] = 0;      f.len[0] = d;
+  f.dst[1] = dwg; f.begin[1] = d;      f.len[1] = d;
+  f.dst[2] = dbg; f.begin[2] = 2 * d;  f.len[2] = 1;
+  col_finalize_kernel<<<(d + 127) / 128, 128, 0, stream>>>(f);
+  return check_launch("col_finalize_kernel");
+}
+
+size_t colsum_workspace_floats(int64_t rows) {
+  (void)rows;
+  return static_cast<size_t>(sm_count()) * 8 * 128;
+}
+
+int colsum_launch(const float* X, int64_t rows, int cols, float* dst, float* partial, cudaStream_t stream) {
+  CGCN_REQUIRE(cols >= 1 && cols <= 128, "colsum: cols=%d", cols);
+  const int64_t max_parts = static_cast<int64_t>(sm_count()) * 8;
+  int64_t rows_per = (rows + max_parts - 1) / max_parts;
+  if (rows_per < 64) rows_per = 64;
+  const int parts = static_cast<int>((rows + rows_per - 1) / rows_per);
+  colsum_partial_kernel<<<parts, 128, 0, stream>>>(X, rows, cols, rows_per, partial);
+  CGCN_TRY(check_launch("colsum_partial_kernel"));
+  ColFinalizeArgs f{};
+  f.partial = partial;
+  f.parts = parts;
+  f.stride = 128;
+  f.dst[0] = dst; f.begin[0] = 0; f.len[0] = cols;
+  col_finalize_kernel<<<1, 128, 0, stream>>>(f);
+  return check_launch("col_finalize_kernel");
+}
+
+int bce_grid() { return sm_count() * 8; }
+
+int bce_launch(const float* out, const float* target, int n, int C, int S, float* probs, float* loss_sum,
+               float* out_grad, float* partial, cudaStream_t stream) {
+  BceArgs a{out, target, probs, out_grad, partial, static_cast<int64_t>(n) * C, C, S,
+            static_cast<float>(1.0 / (static_cast<double>(n) * C))};
+  int grid = static_cast<int>((a.total + 255) / 256);
+  if (grid > bce_grid()) grid = bce_grid();
+  if (grid < 1) grid = 1;
+  bce_kernel<<<grid, 256, 0, stream>>>(a);
+  CGCN_TRY(check_launch("bce_kernel"));
+  bce_finalize_kernel<<<1, 32, 0, stream>>>(partial, grid, a.inv_count, loss_sum);
+  return check_launch("bce_finalize_kernel");
+}
+
+}  // namespace cgcn
+
+using namespace cgcn;
+
+extern "C" size_t cgcn_bce_workspace_bytes(int32_t n, int32_t nclass) {
+  (void)n;
+  (void)nclass;
+  return static_cast<size_t>(bce_grid()) * sizeof(float) + 256;
+}
+
+extern "C" int cgcn_bce_loss(const float* out, const float* target, int32_t n, int32_t nclass, int32_t strands,
+                             float* probs, float* loss_sum_out, float* out_grad, void* workspace,
+                             size_t workspace_bytes, cgcn_stream_t stream) {
+  CGCN_REQUIRE(out && target && loss_sum_out, "cgcn_bce_loss: null argument");
+  CGCN_REQUIRE(n >= 1 && nclass >= 1 && (strands == 1 || strands == 2), "cgcn_bce_loss: bad shape");
+  if (workspace == nullptr || workspace_bytes < cgcn_bce_workspace_bytes(n, nclass)) {
+    set_error("cgcn_bce_loss: workspace too small");
+    return CGCN_ERR_WORKSPACE;
+  }
+  return bce_launch(out, target, n, nclass, strands, probs, loss_sum_out, out_grad, static_cast<float*>(workspace),
+                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cgcn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t count, float lr,
+                             float momentum, float weight_decay, float grad_scale, cgcn_stream_t stream) {
+  CGCN_REQUIRE(params && grads && momentum_buf && count >= 0, "cgcn_sgd_step: null argument");
+  if (count == 0) return CGCN_OK;
+  sgd_kernel<<<static_cast<int>((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params, grads, momentum_buf, count, lr, momentum, weight_decay, grad_scale);
+  return check_launch("sgd_kernel");
+}
+
+extern "C" int cgcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                              float lr, float beta1, float beta2, float eps, int64_t step_index, float grad_scale,
+                              cgcn_stream_t stream) {
+  CGCN_REQUIRE(params && grads && exp_avg && exp_avg_sq && count >= 0 && step_index >= 1, "cgcn_adam_step: bad argument");
+  if (count == 0) return CGCN_OK;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step_index));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step_index));
+  adam_kernel<<<static_cast<int>((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, static_cast<float>(bc1),
+      static_cast<float>(sqrt(bc2)), grad_scale);
+  return check_launch("adam_kernel");
+}
+
+extern "C" int cgcn_interleave_strands(const float* const* src_host, int32_t strands, int32_t n, int32_t d, float* dst,
+                                       cgcn_stream_t stream) {
+  CGCN_REQUIRE(src_host && dst && (strands == 1 || strands == 2) && d % 4 == 0, "cgcn_interleave_strands: bad argument");
+  if (n <= 0) return CGCN_OK;
+  const int64_t total = static_cast<int64_t>(n) * strands * (d / 4);
+  interleave_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src_host[0], strands == 2 ? src_host[1] : src_host[0], strands, n, d / 4, reinterpret_cast<float4*>(dst));
+  return check_launch("interleave_kernel");
+}
+
+extern "C" int cgcn_deinterleave_strands(const float* src, int32_t strands, int32_t n, int32_t width,
+                                         float* const* dst_host, cgcn_stream_t stream) {
+  CGCN_REQUIRE(src && dst_host && (strands == 1 || strands == 2) && width >= 1, "cgcn_deinterleave_strands: bad argument");
+  if (n <= 0) return CGCN_OK;
+  const int64_t total = static_cast<int64_t>(n) * strands * width;
+  deinterleave_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, strands, n, width, dst_host[0], strands == 2 ? dst_host[1] : dst_host[0]);
+  return check_launch("deinterleave_kernel");
+}
+
+extern "C" int cgcn_dropout_mask(float* mask, int32_t n, int32_t strands, int32_t d, float p, uint64_t seed,
+                                 uint64_t step, int32_t site, cgcn_stream_t stream) {
+  CGCN_REQUIRE(mask && d % 4 == 0 && p >= 0.f && p < 1.f, "cgcn_dropout_mask: bad argument");
+  const int64_t total4 = static_cast<int64_t>(n) * strands * d / 4;
+  if (total4 <= 0) return CGCN_OK;
+  const DropoutCfg cfg = make_dropout(p, seed, step, site, true);
+  dropout_mask_kernel<<<flat_grid(total4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(mask), total4, cfg);
+  return check_launch("dropout_mask_kernel");
+}

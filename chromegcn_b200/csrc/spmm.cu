@@ -1,0 +1,186 @@
+// Pattern-only CSR SpMM over a strand-interleaved fp32 feature panel (sm_100a).
+//
+//   out[i,:] = scale_i * sum_{j in row i of bin(A+I)} x[j,:]  (+ residual[i,:])
+//
+// replaces torch.spmm(adj, support) of models/SubLayers.py:46 with adj = D^-1 bin(A+I) built by
+// utils/util_methods.py:99-106,152-165 (scale_mode 1), and its autograd transpose
+// A_hat^T G = P (D^-1 G) (scale_mode 0, the D^-1 having been applied upstream).
+//
+// There is no value array: every stored entry of row i equals 1/deg_i, and deg_i is
+// rowptr[i+1]-rowptr[i], so the kernel's HBM/L2 traffic is colidx + one gathered row per entry
+// + one written row per node.  One warp owns one row; a row of the panel is VEC*512 bytes and
+// each lane reads VEC 128-bit words of it, so a gather is VEC fully coalesced 512 B requests.
+// Column indices are fetched 32 at a time (coalesced) and broadcast by shuffle; 8 independent
+// 128-bit loads per lane are kept in flight.  Summation runs in CSR (ascending column) order,
+// so results are run-to-run deterministic.  Rows longer than LONG_ROW are split over the
+// 8 warps of the CTA and combined in shared memory in a fixed order.
+#include "common.cuh"
+
+namespace cgcn {
+
+constexpr int SPMM_WARPS = 8;
+constexpr int LONG_ROW = 512;
+
+template <int VEC>
+__device__ __forceinline__ void gather_range(const int32_t* __restrict__ colidx, const float* __restrict__ x, int begin,
+                                             int end, int lane, float4 (&acc)[VEC]) {
+  constexpr int UNROLL = (VEC >= 8) ? 1 : (8 / VEC);
+  constexpr size_t PITCH = static_cast<size_t>(VEC) * 128;
+  for (int base = begin; base < end; base += 32) {
+    const int mine = (base + lane < end) ? __ldg(colidx + base + lane) : 0;
+    const int cnt = min(32, end - base);
+    int k = 0;
+    for (; k + UNROLL <= cnt; k += UNROLL) {
+      float4 v[UNROLL][VEC];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int c = __shfl_sync(0xffffffffu, mine, k + u);
+        const float* p = x + static_cast<size_t>(c) * PITCH + lane * 4;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) v[u][q] = ldg4(p + q * 128);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          acc[q].x += v[u][q].x;
+          acc[q].y += v[u][q].y;
+          acc[q].z += v[u][q].z;
+          acc[q].w += v[u][q].w;
+        }
+      }
+    }
+    for (; k < cnt; ++k) {
+      const int c = __shfl_sync(0xffffffffu, mine, k);
+      const float* p = x + static_cast<size_t>(c) * PITCH + lane * 4;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        const float4 v = ldg4(p + q * 128);
+        acc[q].x += v.x;
+        acc[q].y += v.y;
+        acc[q].z += v.z;
+        acc[q].w += v.w;
+      }
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(SPMM_WARPS * 32)
+spmm_pattern_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
+                    const float* __restrict__ x, float* __restrict__ out, int scale_mode,
+                    const float* __restrict__ residual) {
+  constexpr size_t PITCH = static_cast<size_t>(VEC) * 128;
+  __shared__ float4 red[SPMM_WARPS][VEC][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * SPMM_WARPS;
+  const int row = row0 + warp;
+
+  int start = 0, end = 0;
+  if (row < n) {
+    start = __ldg(rowptr + row);
+    end = __ldg(rowptr + row + 1);
+  }
+  const int deg = end - start;
+  if (row < n && deg <= LONG_ROW) {
+    float4 acc[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_range<VEC>(colidx, x, start, end, lane, acc);
+    const float s = (scale_mode == 1 && deg > 0) ? __fdiv_rn(1.0f, static_cast<float>(deg)) : 1.0f;
+    float* o = out + static_cast<size_t>(row) * PITCH + lane * 4;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      float4 r = make_float4(acc[q].x * s, acc[q].y * s, acc[q].z * s, acc[q].w * s);
+      if (residual != nullptr) {
+        const float4 e = ldg4(residual + static_cast<size_t>(row) * PITCH + lane * 4 + q * 128);
+        r.x += e.x;
+        r.y += e.y;
+        r.z += e.z;
+        r.w += e.w;
+      }
+      st4(o + q * 128, r);
+    }
+  }
+
+  // hub rows: any row of this CTA longer than LONG_ROW is shared by all 8 warps
+  const int any_long = __syncthreads_or(row < n && deg > LONG_ROW);
+  if (!any_long) return;
+  for (int r = 0; r < SPMM_WARPS; ++r) {
+    const int lrow = row0 + r;
+    if (lrow >= n) break;                                     // uniform across the CTA
+    const int ls = __ldg(rowptr + lrow), le = __ldg(rowptr + lrow + 1);
+    const int ldeg = le - ls;
+    if (ldeg <= LONG_ROW) continue;                           // uniform across the CTA
+    const int chunk = (ldeg + SPMM_WARPS - 1) / SPMM_WARPS;
+    const int b = min(ls + warp * chunk, le), e = min(b + chunk, le);
+    float4 acc[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_range<VEC>(colidx, x, b, e, lane, acc);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) red[warp][q][lane] = acc[q];
+    __syncthreads();
+    if (warp == 0) {
+      const float s = (scale_mode == 1) ? __fdiv_rn(1.0f, static_cast<float>(ldeg)) : 1.0f;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        float4 t = red[0][q][lane];
+        for (int w = 1; w < SPMM_WARPS; ++w) {
+          const float4 u = red[w][q][lane];
+          t.x += u.x;
+          t.y += u.y;
+          t.z += u.z;
+          t.w += u.w;
+        }
+        t = make_float4(t.x * s, t.y * s, t.z * s, t.w * s);
+        if (residual != nullptr) {
+          const float4 e4 = ldg4(residual + static_cast<size_t>(lrow) * PITCH + lane * 4 + q * 128);
+          t.x += e4.x;
+          t.y += e4.y;
+          t.z += e4.z;
+          t.w += e4.w;
+        }
+        st4(out + static_cast<size_t>(lrow) * PITCH + lane * 4 + q * 128, t);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int scale_mode, const float* residual,
+                cudaStream_t stream) {
+  CGCN_REQUIRE(g != nullptr && g->rowptr != nullptr && (g->colidx != nullptr || g->nnz == 0), "cgcn_spmm: null graph");
+  CGCN_REQUIRE(x != nullptr && out != nullptr, "cgcn_spmm: null panel");
+  CGCN_REQUIRE(x != out, "cgcn_spmm: in-place aggregation is not possible");
+  CGCN_REQUIRE(scale_mode == 0 || scale_mode == 1, "cgcn_spmm: scale_mode %d", scale_mode);
+  CGCN_REQUIRE(width > 0 && width % 128 == 0 && width <= 1024, "cgcn_spmm: width %d must be a multiple of 128, <= 1024", width);
+  if (g->n <= 0) return CGCN_OK;
+  const int vec = width / 128;
+  const dim3 grid((g->n + SPMM_WARPS - 1) / SPMM_WARPS), block(SPMM_WARPS * 32);
+#define SPMM_CASE(V)                                                                                              \
+  case V:                                                                                                         \
+    spmm_pattern_kernel<V><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, x, out, scale_mode, residual); \
+    break;
+  switch (vec) {
+    SPMM_CASE(1)
+    SPMM_CASE(2)
+    SPMM_CASE(3)
+    SPMM_CASE(4)
+    SPMM_CASE(6)
+    SPMM_CASE(8)
+    default:
+      set_error("cgcn_spmm: unsupported width %d", width);
+      return CGCN_ERR_INVALID;
+  }
+#undef SPMM_CASE
+  return check_launch("spmm_pattern_kernel");
+}
+
+}  // namespace cgcn
+
+extern "C" int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, int32_t scale_mode,
+                         const float* residual, cgcn_stream_t stream) {
+  return cgcn::spmm_launch(g, x, out, width, scale_mode, residual, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,154 @@
+"""The fused chromosome step: both strands of one chromosome through the gated GCN, loss,
+backward -- one C-ABI call (`cgcn_train_step`) on a strand-interleaved `[n, 2, d]` panel.
+
+Reference: the body of the chromosome loop, finetune.py:30-53.  What differs by design:
+  * `x_f` / `x_r` are processed together (every column index of the graph is read once per layer
+    for both strands); BatchNorm statistics and running-stat updates stay per strand, in the
+    reference's order (forward strand first);
+  * parameters and gradients live in one flat buffer each (16-byte aligned slots) so the
+    optimiser is one kernel and the data-parallel all-reduce is one NCCL call;
+  * nothing is synchronised: the loss goes to a device slot, probabilities into a caller-provided
+    device buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, ops
+from .chrome_models import ChromeGCN, build_model_struct
+from .graph import HiCGraph
+
+_SLOT = 64  # floats: every parameter starts on a 256-byte boundary inside the flat buffer
+
+
+class FlatParams:
+    """Re-homes a ChromeGCN's parameters (and their .grad) as views into two flat fp32 buffers.
+    `ensure()` is cheap and idempotent; it re-flattens after `.cuda()`, `load_state_dict` or a
+    `.data = ...` assignment (main.py:78-81 does the latter) moved a parameter elsewhere."""
+
+    def __init__(self, model: ChromeGCN):
+        self.model = model
+        self.flat: Optional[torch.Tensor] = None
+        self.flat_grad: Optional[torch.Tensor] = None
+        self.offsets: Dict[str, int] = {}
+        self.total = 0
+
+    def _layout(self, params: Dict[str, torch.nn.Parameter], names: List[str]):
+        off, offsets = 0, {}
+        for k in names:
+            offsets[k] = off
+            off += (params[k].numel() + _SLOT - 1) // _SLOT * _SLOT
+        return offsets, off
+
+    def ensure(self) -> "FlatParams":
+        names = self.model._param_names()
+        params = dict(self.model.named_parameters())
+        dev = params[names[0]].device
+        if dev.type != "cuda":
+            raise _lib.ChromeGCNNativeError("ChromeGCN parameters must be on a CUDA device (no CPU fallback)")
+        offsets, total = self._layout(params, names)
+        ok = (self.flat is not None and self.flat.device == dev and total == self.total and
+              all(params[k].data_ptr() == self.flat.data_ptr() + 4 * offsets[k] and params[k].dtype == torch.float32
+                  for k in names))
+        if not ok:
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            for k in names:
+                p = params[k]
+                view = flat[offsets[k]: offsets[k] + p.numel()].view(p.shape)
+                view.copy_(p.data.to(torch.float32))
+                p.data = view
+            self.flat, self.offsets, self.total = flat, offsets, total
+            self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.attach_grads()
+        return self
+
+    def attach_grads(self) -> None:
+        params = dict(self.model.named_parameters())
+        for k, off in self.offsets.items():
+            p = params[k]
+            want = self.flat_grad[off: off + p.numel()].view(p.shape)
+            if p.grad is None or p.grad.data_ptr() != want.data_ptr():
+                p.grad = want
+
+    def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        params = dict(self.model.named_parameters())
+        return {k: flat[off: off + params[k].numel()].view(params[k].shape) for k, off in self.offsets.items()}
+
+
+def flat_params(model: ChromeGCN) -> FlatParams:
+    st = getattr(model, "_flat_state", None)
+    if st is None:
+        st = FlatParams(model)
+        object.__setattr__(model, "_flat_state", st)
+    return st.ensure()
+
+
+class ChromosomeEngine:
+    """Owns the device buffers of the fused step and grows them to the largest chromosome seen."""
+
+    def __init__(self, model: ChromeGCN, strands: int = 2):
+        self.model = model
+        self.strands = strands
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self.step_count = 0
+
+    def _buf(self, name: str, numel: int, dtype=torch.float32) -> torch.Tensor:
+        t = self._bufs.get(name)
+        dev = next(self.model.parameters()).device
+        if t is None or t.numel() < numel or t.device != dev:
+            t = torch.empty(max(numel, 1), dtype=dtype, device=dev)
+            self._bufs[name] = t
+        return t
+
+    def panel(self, n: int, d: int) -> torch.Tensor:
+        return self._buf("panel", n * self.strands * d)[: n * self.strands * d].view(n, self.strands, d)
+
+    def pack(self, x_f: torch.Tensor, x_r: torch.Tensor) -> torch.Tensor:
+        """[n, d] x 2 (device) -> the [n, 2, d] panel."""
+        n, d = x_f.shape
+        return ops.interleave_strands([x_f, x_r], out=self.panel(n, d))
+
+    def run(self, graph: HiCGraph, panel: torch.Tensor, target: torch.Tensor, probs_out: Optional[torch.Tensor],
+            loss_slot: torch.Tensor, train: bool, input_grad: Optional[torch.Tensor] = None):
+        """One chromosome: forward (+ loss, + backward when `train`).  Gradients land in the model's flat
+        gradient buffer (== every parameter's .grad).  Returns `(out [n, S, C], gates)` views that stay
+        valid until the next call."""
+        lib = _lib.load()
+        model = self.model
+        fp = flat_params(model)
+        S = self.strands
+        n, d = panel.shape[0], panel.shape[-1]
+        nclass, layers = model.out.out_features, model.num_layers
+        dev = panel.device
+        with torch.cuda.device(dev):
+            ws_bytes = lib.cgcn_model_workspace_bytes(n, d, nclass, layers, S)
+            if ws_bytes == 0:
+                raise _lib.ChromeGCNNativeError("cgcn_model_workspace_bytes rejected n=%d d=%d" % (n, d))
+            ws = self._buf("ws", ws_bytes // 4)
+            out = self._buf("out", n * S * nclass)[: n * S * nclass].view(n, S, nclass)
+            gates = [self._buf("gate%d" % l, n * S)[: n * S].view(n, S) for l in range(layers)]
+            dout = self._buf("dout", n * S * nclass)[: n * S * nclass].view(n, S, nclass)
+            seed, step = model._next_dropout_counter() if model.training else (0, 0)
+            bn = model.batch_norm
+            params = fp.views(fp.flat)
+            grads = fp.views(fp.flat_grad)
+            m = build_model_struct(graph, d, nclass, layers, S, model.training, model.dropout, seed, step, params,
+                                   grads if train else None, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                   panel, input_grad, out, gates, None, ws, model.gemm_impl,
+                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+            tgt = ops._f32c(target)
+            if train:
+                _lib.check(lib.cgcn_train_step(C.byref(m), tgt.data_ptr(), _lib.ptr(probs_out), loss_slot.data_ptr(),
+                                               dout.data_ptr()), "cgcn_train_step")
+                fp.attach_grads()
+            else:
+                _lib.check(lib.cgcn_model_forward(C.byref(m)), "cgcn_model_forward")
+                bce_ws = self._buf("bce_ws", lib.cgcn_bce_workspace_bytes(n, nclass) // 4 + 64)
+                _lib.check(lib.cgcn_bce_loss(out.data_ptr(), tgt.data_ptr(), n, nclass, S, _lib.ptr(probs_out),
+                                             loss_slot.data_ptr(), None, bce_ws.data_ptr(), bce_ws.numel() * 4,
+                                             _lib.current_stream()), "cgcn_bce_loss")
+        self.step_count += 1
+        return out, gates

@@ -7,9 +7,9 @@ measured number is taken on inputs produced here:
                shape `data/1create_windows.py:49-59` of the reference produces),
                N_c = round(20000 * len_c / len_chr22) windows per chromosome;
 * contacts  -- a Juicer `RAWobserved`-like triplet list `(bin1, bin2, count)` in
-               ascending `(bin1, bin2)` order, genomic distance drawn from a
-               P(s) ~ 1/s law, integer counts (the input of
-               `data/7create_graph_new.py:67-91`);
+               ascending `(bin1, bin2)` order, genomic distance log-uniform (contact
+               density P(s) ~ 1/s), integer counts that decay with distance (the input
+               of `data/7create_graph_new.py:67-91`);
 * norm      -- a Juicer `*.SQRTVCnorm`-like per-bin vector with a few NaN and
                0.0 entries (`data/7create_graph_new.py:51-65`);
 * features  -- N(0,1) fp32 `[N, 128]` forward / reverse-complement features and
@@ -83,21 +83,32 @@ def make_windows(chrom: str, scale: float = 1.0, n_windows: Optional[int] = None
 def make_hic(chrom: str, hic_edges: int = 500000, scale: float = 1.0,
              candidates_per_edge: float = 8.0, n_windows: Optional[int] = None,
              n_bins: Optional[int] = None, max_dist_bins: int = 2000) -> SyntheticHiC:
-    """Distance-decay contact list for one chromosome."""
+    """Distance-decay contact list for one chromosome.
+
+    `candidates_per_edge * K` draws (K = hic_edges / 2 undirected pairs): bin1 uniform over the
+    window bins, genomic distance log-uniform in [1, max_dist_bins] bins (contact density
+    P(s) ~ 1/s), about 15 % of the rows then get a non-window bin1 so the window filter of
+    `data/7create_graph_new.py:78` has something to reject; integer counts
+    max(1, Poisson(60/s) + Geometric(0.3)) so near-diagonal contacts dominate the top-K but ties are
+    everywhere; rows ordered by (bin1, bin2) with duplicates summed, like a Juicer dump.
+    """
     c = chrom_index(chrom)
     if n_bins is None:
         n_bins = int(HG19_LENGTHS[chrom] * scale) // BIN_BP
     windows = make_windows(chrom, scale, n_windows, n_bins)
+    wbins = windows // BIN_BP
     rng = np.random.default_rng(2000 + c)
     k_pairs = int(hic_edges / 2.0)
     m = int(candidates_per_edge * k_pairs)
-    b1 = rng.integers(0, n_bins - 1, size=m, dtype=np.int64)
-    # P(s) ~ s^-1: floor(Pareto(alpha=1)) + 1, clipped
-    dist = np.minimum(np.floor(rng.pareto(1.0, size=m)).astype(np.int64) + 1, max_dist_bins)
-    b2 = np.minimum(b1 + dist, n_bins - 1)
-    keep = b2 > b1
-    b1, b2 = b1[keep], b2[keep]
-    counts = rng.geometric(0.2, size=b1.shape[0]).astype(np.float64)  # 1 + Geometric
+    b1 = wbins[rng.integers(0, wbins.shape[0], size=m)]
+    off = rng.random(m) < 0.15
+    b1 = np.where(off, rng.integers(0, n_bins - 1, size=m, dtype=np.int64), b1)
+    dist = np.floor(np.exp(rng.random(m) * np.log(max_dist_bins + 1.0))).astype(np.int64)
+    dist = np.clip(dist, 1, max_dist_bins)
+    b2 = b1 + dist
+    keep = b2 < n_bins
+    b1, b2, dist = b1[keep], b2[keep], dist[keep]
+    counts = np.maximum(1, rng.poisson(60.0 / dist) + rng.geometric(0.3, size=b1.shape[0]) - 1).astype(np.float64)
     # Juicer dumps are ordered by (bin1, bin2); duplicates collapse (counts add)
     key = b1 * np.int64(n_bins) + b2
     order = np.argsort(key, kind="stable")
@@ -131,11 +142,11 @@ def make_pattern_direct(n: int, k_pairs: int, seed: int, max_dist: int = 2000):
     scipy CSR (float64 ones, zero diagonal) the reference's pickles would hold."""
     from scipy import sparse
     rng = np.random.default_rng(seed)
-    m = int(k_pairs * 1.15)
+    m = int(k_pairs * 1.5)
     i = rng.integers(0, n - 1, size=m, dtype=np.int64)
-    dist = np.minimum(np.floor(rng.pareto(1.0, size=m)).astype(np.int64) + 1, max_dist)
-    j = np.minimum(i + dist, n - 1)
-    keep = j > i
+    dist = np.clip(np.floor(np.exp(rng.random(m) * np.log(max_dist + 1.0))).astype(np.int64), 1, max_dist)
+    j = i + dist
+    keep = j < n
     key = np.unique(i[keep] * np.int64(n) + j[keep])
     if key.shape[0] > k_pairs:
         key = rng.choice(key, size=k_pairs, replace=False)

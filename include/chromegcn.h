@@ -1,0 +1,248 @@
+/*
+ * chromegcn.h -- C ABI of libchromegcn.so: the B200 (sm_100a) implementation of the
+ * ChromeGCN chromosome-model hot path.
+ *
+ * The reference (QData/ChromeGCN) is pure Python/PyTorch and has no FFI of its own; its
+ * hot path is nn.Module code.  This header is therefore the boundary a maintainer binds
+ * (ctypes stub in INTEGRATION.md) to put the CUDA path behind the reference's Python
+ * surface.  Each entry point names the reference code it replaces (paths relative to the
+ * reference repository).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - every call enqueues work on the caller's stream (a cudaStream_t passed as void*) and
+ *     neither allocates nor synchronises, except cgcn_adj_build / cgcn_coo_to_pattern, whose
+ *     output size is data dependent (they synchronise `stream` before returning);
+ *   - return value: 0 = ok, negative = error (cgcn_status); cgcn_last_error() returns a
+ *     thread-local message for the last failing call of the calling thread;
+ *   - thread-safe for distinct streams / buffers; no global mutable state but that string;
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute call
+ *     returns CGCN_ERR_CUDA.
+ *
+ * Feature panels are row-major fp32 `[n][strands][d]` ("strand-interleaved": the forward
+ * and reverse-complement feature rows of one window sit next to each other, so one column
+ * index of the graph fetches strands*d*4 contiguous bytes).  strands = 1 is the layout of a
+ * plain `[n][d]` tensor.  The SpMM takes any row width that is a multiple of 128 floats up to
+ * 1024; the model entry points take d = 128 (the reference fixes it, main.py:62).
+ */
+#ifndef CHROMEGCN_H_
+#define CHROMEGCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGCN_ABI_VERSION 1
+
+typedef void* cgcn_stream_t; /* cudaStream_t */
+
+typedef enum cgcn_status {
+  CGCN_OK = 0,
+  CGCN_ERR_INVALID = -1,   /* bad argument (null pointer, unsupported d, ...) */
+  CGCN_ERR_CUDA = -2,      /* CUDA runtime error, no device, wrong architecture */
+  CGCN_ERR_WORKSPACE = -3, /* workspace too small */
+  CGCN_ERR_DATA = -4,      /* input data violates the contract (NaN contact value, norm index out of range, ...) */
+  CGCN_ERR_CAPACITY = -5   /* output buffer too small */
+} cgcn_status;
+
+/* ---------------------------------------------------------------- library ---- */
+int cgcn_abi_version(void);
+const char* cgcn_last_error(void);
+/* SM count and compute capability of the current device. */
+int cgcn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* sizeof() of the structs below as compiled, for binding self-checks: which = 0 cgcn_graph,
+ * 1 cgcn_params, 2 cgcn_model. */
+size_t cgcn_sizeof(int32_t which);
+/* Number of kernels this library has launched from the calling process (all threads). */
+int64_t cgcn_launch_count(void);
+
+/* ------------------------------------------------- piece 1: adjacency build ---- */
+/*
+ * Hi-C contact list -> symmetric binary window adjacency in CSR (no self loops).
+ * Replaces data/7create_graph_new.py:67-120 (get_contact_edge_pairs, get_top_contact_locs,
+ * create_adj_mat) bit-exactly:
+ *   keep rows with bin1 != bin2 and both bins in `window_starts` (sorted, unique);
+ *   use_norm: v = val / (nv[bin1 / res_bp] * nv[bin2 / res_bp]) in IEEE double, nv = norm with
+ *   NaN and 0.0 replaced by +inf (:51-65);  !use_norm: only the first k_pairs accepted rows (:88-89);
+ *   duplicate (bin1,bin2) keys: rank position = first occurrence, value = last occurrence (:86);
+ *   stable descending sort by v, first k_pairs entries (all if k_pairs == 0) (:93-104);
+ *   emit (i,j) and (j,i), collapse duplicates, CSR with ascending columns (:108-120).
+ * rowptr has n+1 entries; colidx capacity colidx_cap entries (2*k_pairs always suffices when
+ * k_pairs > 0).  *nnz_host (host pointer) receives the number of stored entries.
+ * A NaN contact value or a bin beyond norm_len is CGCN_ERR_DATA (the reference's behaviour there
+ * is a Python exception / an undefined sort order).
+ */
+int cgcn_adj_build_workspace_bytes(int64_t m, int64_t n, int64_t k_pairs, size_t* bytes_host);
+int cgcn_adj_build(const int64_t* bin1, const int64_t* bin2, const double* val, int64_t m,
+                   const int64_t* window_starts, int64_t n,
+                   const double* norm, int64_t norm_len, int64_t res_bp,
+                   int64_t k_pairs, int32_t use_norm,
+                   int32_t* rowptr, int32_t* colidx, int64_t colidx_cap, int64_t* nnz_host,
+                   void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
+
+/*
+ * Pattern of bin(A + I): merges the diagonal into every (column-sorted) CSR row.
+ * Replaces the structural half of process_graph('hic') (utils/util_methods.py:152-165); the
+ * numeric half, D^-1, is never materialised: every kernel derives 1/deg_i from rowptr.
+ * rowptr_out: n+1 entries; colidx_out: nnz + n entries (an existing diagonal entry is merged:
+ * the unused tail is left untouched and rowptr_out[n] is the true count).
+ */
+int cgcn_adj_add_selfloops_workspace_bytes(int32_t n, size_t* bytes_host);
+int cgcn_adj_add_selfloops(const int32_t* rowptr, const int32_t* colidx, int32_t n,
+                           int32_t* rowptr_out, int32_t* colidx_out,
+                           void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
+
+/*
+ * torch sparse COO (int64 rows/cols, fp32 values, any order) -> CSR pattern, for callers that
+ * hand ChromeGCN.forward the tensor the reference's process_graph returns
+ * (utils/util_methods.py:120-135).  flags_host bit 0: every value equals 1/deg(row) (mean
+ * aggregation: pattern-only fast path is exact); bit 1: pattern is symmetric.
+ * Workspace: cgcn_coo_to_pattern_workspace_bytes(nnz, n).  Synchronises `stream`.
+ */
+int cgcn_coo_to_pattern_workspace_bytes(int64_t nnz, int64_t n, size_t* bytes_host);
+int cgcn_coo_to_pattern(const int64_t* rows, const int64_t* cols, const float* vals, int64_t nnz, int32_t n,
+                        int32_t* rowptr, int32_t* colidx, int32_t* flags_host,
+                        void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
+
+/* ------------------------------------------------------- piece 2: the SpMM ---- */
+typedef struct cgcn_graph {
+  int32_t n;             /* windows (rows) */
+  int32_t nnz;           /* stored entries of bin(A+I) */
+  const int32_t* rowptr; /* [n+1] */
+  const int32_t* colidx; /* [nnz], ascending inside a row */
+} cgcn_graph;
+
+/*
+ * out[i,:] = scale_i * sum_{j in row i} x[j,:]  (+ residual[i,:])
+ *   scale_mode 0: scale_i = 1           (backward: A_hat^T G = P (D^-1 G), D^-1 folded upstream)
+ *   scale_mode 1: scale_i = 1/deg_i     (forward mean aggregation, torch.spmm(adj, .) of
+ *                                        models/SubLayers.py:46 with adj = D^-1 bin(A+I))
+ * width = floats per row (strands*d), a multiple of 128.  residual may be NULL.
+ */
+int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, int32_t scale_mode,
+              const float* residual, cgcn_stream_t stream);
+
+/* ------------------------------------------------ piece 3: dense contractions ---- */
+/* gemm_impl: 0 = auto (tcgen05 when the shape allows), 1 = fp32 FFMA kernel, 2 = tcgen05 3xTF32. */
+/*
+ * C[m x n] = rowscale * (A[m x k] * op(B)) + bias.   A row-major (lda), C row-major (ldc).
+ * b_transposed 0: B is [k][n] row-major (torch.mm(input, weight), models/SubLayers.py:43);
+ * b_transposed 1: B is [n][k] row-major (nn.Linear weight, models/ChromeModels.py:51).
+ * bias [n] or NULL.  rowscale_rowptr: NULL, or the graph's rowptr: row r is scaled by
+ * 1/deg(r / rowscale_group) (the D^-1 of A_hat^T applied to the input of the backward SpMM).
+ * k, n <= 128.
+ */
+int cgcn_gemm_rowpanel(const float* A, int64_t lda, const float* B, int32_t b_transposed, const float* bias,
+                       float* C, int64_t ldc, int64_t m, int32_t n, int32_t k,
+                       const int32_t* rowscale_rowptr, int32_t rowscale_group,
+                       int32_t gemm_impl, void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
+/*
+ * C[ka x nb] (+)= sum_r A[r][0:ka] (x) B[r][0:nb]   (weight gradients X^T G: a reduction over
+ * all m rows; autograd of models/SubLayers.py:43 and models/ChromeModels.py:51).
+ * Deterministic: per-CTA partial tiles in the workspace, reduced in a fixed order in fp64.
+ * accumulate != 0 adds to C.  ka, nb <= 128.
+ */
+size_t cgcn_gemm_gram_workspace_bytes(int64_t m);
+int cgcn_gemm_gram(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t m, int32_t ka, int32_t nb, int32_t accumulate,
+                   int32_t gemm_impl, void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
+
+/* ----------------------------------- the model: forward / backward / train step ---- */
+/* Parameters in the reference's state_dict order and shapes (models/ChromeModels.py:22-31):
+ * GC{1,2}.weight [d][d] (in x out), GC{1,2}.bias [d], W{1,2}.weight [1][d], W{1,2}.bias [1],
+ * batch_norm.weight/bias [d], out.weight [nclass][d], out.bias [nclass].  A second instance of
+ * this struct holds the gradients. */
+typedef struct cgcn_params {
+  float* gc_w[2];
+  float* gc_b[2];
+  float* gate_w[2];
+  float* gate_b[2];
+  float* bn_w;
+  float* bn_b;
+  float* out_w;
+  float* out_b;
+} cgcn_params;
+
+typedef struct cgcn_model {
+  cgcn_graph graph;
+  int32_t d;              /* feature width, multiple of 128 */
+  int32_t nclass;         /* <= 128 */
+  int32_t layers;         /* 1 or 2 (the reference builds 2 iff gcn_layers == 2) */
+  int32_t strands;        /* 1 = one forward() call; 2 = x_f and x_r of finetune.py:41-42 batched */
+  int32_t training;       /* BatchNorm batch statistics + dropout (ChromeModel.train()) */
+  int32_t gemm_impl;      /* see above */
+  int32_t need_input_grad;/* also produce d loss / d x_in (finetune.py:33-34 asks, nothing reads it) */
+  int32_t reserved0;
+  float dropout_p;        /* F.dropout p (models/ChromeModels.py:42,50) */
+  float bn_momentum;      /* 0.1 */
+  float bn_eps;           /* 1e-5 */
+  float reserved1;
+  uint64_t seed;          /* dropout: keep-mask is a pure function of (seed, step, site, element) */
+  uint64_t step;
+  cgcn_params params;
+  cgcn_params grads;      /* written (not accumulated) by backward */
+  float* bn_running_mean; /* [d] */
+  float* bn_running_var;  /* [d] */
+  int64_t* bn_num_batches_tracked; /* [1] */
+  const float* x_in;      /* [n][strands][d] */
+  float* x_in_grad;       /* [n][strands][d] or NULL */
+  float* out;             /* [n][strands][nclass] logits (models/ChromeModels.py:51) */
+  float* gate[2];         /* [n][strands] g, g2 (models/ChromeModels.py:39,45) */
+  const float* out_grad;  /* [n][strands][nclass], input of backward */
+  float* workspace;       /* cgcn_model_workspace_bytes() bytes, kept from forward to backward */
+  size_t workspace_bytes;
+  cgcn_stream_t stream;
+} cgcn_model;
+
+size_t cgcn_model_workspace_bytes(int32_t n, int32_t d, int32_t nclass, int32_t layers, int32_t strands);
+/* ChromeGCN.forward (models/ChromeModels.py:34-52) for `strands` feature sets at once. */
+int cgcn_model_forward(const cgcn_model* m);
+/* autograd of the same: fills m->grads (and x_in_grad) from m->out_grad and the workspace. */
+int cgcn_model_backward(const cgcn_model* m);
+
+/*
+ * finetune.py:43-45,52: pred = mean over strands of the logits; loss = BCE-with-logits, mean over
+ * n x nclass; probs = sigmoid(pred).  Writes loss_sum_out[0] += loss (a device accumulator, like
+ * `total_loss += loss.item()` without the sync), probs [n][nclass] (may be NULL), and, if
+ * out_grad != NULL, d loss / d out [n][strands][nclass].
+ */
+size_t cgcn_bce_workspace_bytes(int32_t n, int32_t nclass);
+int cgcn_bce_loss(const float* out, const float* target, int32_t n, int32_t nclass, int32_t strands,
+                  float* probs, float* loss_sum_out, float* out_grad,
+                  void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
+
+/* One iteration of the chromosome loop of finetune.py:39-53 for split == 'train':
+ * forward (both strands), loss, backward.  The optimiser step is cgcn_sgd_step / cgcn_adam_step. */
+int cgcn_train_step(const cgcn_model* m, const float* target, float* probs, float* loss_sum_out,
+                    float* out_grad_scratch);
+
+/* ------------------------------------------------------------- optimiser ---- */
+/* torch.optim.SGD(lr, momentum, weight_decay) as built by utils/util_methods.py:18-19, over one flat
+ * buffer: g += wd*p ; buf = momentum*buf + g ; p -= lr*buf.  grad_scale multiplies g first (1/world
+ * for data-parallel averaging, else 1). */
+int cgcn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t count,
+                  float lr, float momentum, float weight_decay, float grad_scale, cgcn_stream_t stream);
+/* torch.optim.Adam(lr, betas) as built by utils/util_methods.py:16-17 (eps 1e-8, no weight decay);
+ * step_index counts from 1. */
+int cgcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                   float lr, float beta1, float beta2, float eps, int64_t step_index, float grad_scale,
+                   cgcn_stream_t stream);
+
+/* --------------------------------------------------------------- utilities ---- */
+/* [n][d] x strands  <->  [n][strands][d].  src/dst arrays of `strands` pointers are HOST arrays. */
+int cgcn_interleave_strands(const float* const* src_host, int32_t strands, int32_t n, int32_t d, float* dst,
+                            cgcn_stream_t stream);
+int cgcn_deinterleave_strands(const float* src, int32_t strands, int32_t n, int32_t width, float* const* dst_host,
+                              cgcn_stream_t stream);
+/* The keep-mask (0 or 1/(1-p)) the model draws at dropout site `site` (0: between the layers,
+ * 1: after BatchNorm) for (seed, step): lets a test inject the same mask into the oracle. */
+int cgcn_dropout_mask(float* mask, int32_t n, int32_t strands, int32_t d, float p, uint64_t seed, uint64_t step,
+                      int32_t site, cgcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROMEGCN_H_ */

@@ -1,0 +1,283 @@
+"""GPU parity of the model path against the golden vectors minted from the live reference
+(tests/golden/make_golden.py) and against the CPU oracle on larger seeded inputs.
+
+Tolerance rule (stated once, used everywhere):
+  * forward quantities (logits, gates, loss, probabilities, BatchNorm running stats):
+        max|a-b| / max|b|  <=  1e-5   against the reference's fp32 output;
+  * gradients: error against the reference's fp64 output <= max(1e-5, 3 x the fp32 reference's own
+    error against fp64) -- sums of signed terms over all rows (bias / gate-bias gradients) cancel,
+    and the fp32 reference itself is only 1e-5 .. 2e-3 accurate there (tests/test_oracle_golden.py);
+  * per-label AUROC / AUPR: <= 1e-4 absolute.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import gcn as ogcn
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+FWD_TOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _grad_ok(name, got, z, prefix="grad."):
+    ref64 = torch.from_numpy(z["f64." + prefix + name])
+    own = ogcn.max_rel(torch.from_numpy(z["f32." + prefix + name]), ref64)
+    err = ogcn.max_rel(got.detach().cpu(), ref64)
+    assert err <= max(1e-5, 3 * own), "%s: err %.3e (fp32 reference's own %.3e)" % (name, err, own)
+    return err
+
+
+def _load(z, layers, dropout=0.0):
+    from chromegcn_b200.chrome_models import ChromeGCN
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0.")}
+    m = ChromeGCN(128, 128, sd["out.weight"].shape[0], dropout, True, layers)
+    missing = m.load_state_dict(sd)          # the reference's state_dict loads as is
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.to(_dev())
+
+
+def _graph(z):
+    from chromegcn_b200.graph import HiCGraph
+    return HiCGraph.from_csr_pattern(z["indptr"], z["indices"], _dev())
+
+
+@pytest.mark.parametrize("tag", ["l2_ref", "l2_stress", "l1_stress"])
+def test_module_api_matches_reference(tag):
+    """ChromeGCN.forward called exactly like finetune.py:41-45 (two calls, torch loss, autograd)."""
+    z = np.load(os.path.join(GOLDEN, "model_%s.npz" % tag))
+    layers = int(z["layers"])
+    m = _load(z, layers)
+    g = _graph(z)
+    x_f = torch.from_numpy(z["x_f"]).to(_dev())
+    x_r = torch.from_numpy(z["x_r"]).to(_dev())
+    tgt = torch.from_numpy(z["target"]).to(_dev())
+
+    m.eval()
+    with torch.no_grad():
+        xin, out, (g1, g2), last = m(x_f, g, None)
+    assert xin is x_f and last is None
+    assert ogcn.max_rel(out.cpu(), torch.from_numpy(z["f32.eval.out_f"])) <= FWD_TOL
+    assert ogcn.max_rel(g1.cpu(), torch.from_numpy(z["f32.eval.g1_f"])) <= FWD_TOL
+    assert g1.shape == (x_f.shape[0], 1)
+    if layers == 2:
+        assert ogcn.max_rel(g2.cpu(), torch.from_numpy(z["f32.eval.g2_f"])) <= FWD_TOL
+    else:
+        assert g2 is None
+
+    m.train()
+    x_f.requires_grad_(True)
+    x_r.requires_grad_(True)
+    _, pf, (g1f, g2f), _ = m(x_f, g, None)
+    _, pr, (g1r, g2r), _ = m(x_r, g, None)
+    pred = (pf + pr) / 2
+    loss = F.binary_cross_entropy_with_logits(pred, tgt)
+    loss.backward()
+    assert ogcn.max_rel(pred.detach().cpu(), torch.from_numpy(z["f32.train.pred"])) <= FWD_TOL
+    assert abs(loss.item() - float(z["f32.train.loss"])) <= FWD_TOL * abs(float(z["f32.train.loss"]))
+    assert ogcn.max_rel(g1r.cpu(), torch.from_numpy(z["f32.train.g1_r"])) <= FWD_TOL
+    for k, p in m.named_parameters():
+        _grad_ok(k, p.grad, z)
+    _grad_ok("xgrad_f", x_f.grad, z, prefix="train.")
+    _grad_ok("xgrad_r", x_r.grad, z, prefix="train.")
+    bn = m.batch_norm
+    assert ogcn.max_rel(bn.running_mean.cpu(), torch.from_numpy(z["f32.after.batch_norm.running_mean"])) <= FWD_TOL
+    assert ogcn.max_rel(bn.running_var.cpu(), torch.from_numpy(z["f32.after.batch_norm.running_var"])) <= FWD_TOL
+    assert int(bn.num_batches_tracked) == 2
+
+
+@pytest.mark.parametrize("tag", ["l2_ref", "l2_stress", "l1_stress"])
+def test_fused_engine_matches_reference(tag):
+    """Both strands batched in one cgcn_train_step call (what finetune() uses)."""
+    from chromegcn_b200.engine import ChromosomeEngine, flat_params
+    z = np.load(os.path.join(GOLDEN, "model_%s.npz" % tag))
+    layers = int(z["layers"])
+    m = _load(z, layers)
+    m.train()
+    g = _graph(z)
+    eng = ChromosomeEngine(m, 2)
+    panel = eng.pack(torch.from_numpy(z["x_f"]).to(_dev()), torch.from_numpy(z["x_r"]).to(_dev()))
+    tgt = torch.from_numpy(z["target"]).to(_dev())
+    n, c = tgt.shape
+    probs = torch.empty(n, c, device=_dev())
+    loss = torch.zeros(1, device=_dev())
+    xg = torch.empty_like(panel)
+    out, gates = eng.run(g, panel, tgt, probs, loss, train=True, input_grad=xg)
+    pred = out.mean(1)
+    assert ogcn.max_rel(pred.cpu(), torch.from_numpy(z["f32.train.pred"])) <= FWD_TOL
+    assert ogcn.max_rel(probs.cpu(), torch.sigmoid(torch.from_numpy(z["f32.train.pred"]))) <= FWD_TOL
+    assert abs(loss.item() - float(z["f32.train.loss"])) <= FWD_TOL * abs(float(z["f32.train.loss"]))
+    assert ogcn.max_rel(gates[0][:, 0].cpu(), torch.from_numpy(z["f32.train.g1_f"])[:, 0]) <= FWD_TOL
+    assert ogcn.max_rel(gates[0][:, 1].cpu(), torch.from_numpy(z["f32.train.g1_r"])[:, 0]) <= FWD_TOL
+    if layers == 2:
+        assert ogcn.max_rel(gates[1][:, 1].cpu(), torch.from_numpy(z["f32.train.g2_r"])[:, 0]) <= FWD_TOL
+    for k, p in m.named_parameters():
+        _grad_ok(k, p.grad, z)
+    _grad_ok("xgrad_f", xg[:, 0], z, prefix="train.")
+    _grad_ok("xgrad_r", xg[:, 1], z, prefix="train.")
+    assert ogcn.max_rel(m.batch_norm.running_var.cpu(), torch.from_numpy(z["f32.after.batch_norm.running_var"])) <= FWD_TOL
+    assert int(m.batch_norm.num_batches_tracked) == 2
+    # parameters are views of one flat buffer and .grad of one flat gradient buffer
+    fp = flat_params(m)
+    assert all(p.data_ptr() >= fp.flat.data_ptr() and p.data_ptr() < fp.flat.data_ptr() + 4 * fp.total
+               for p in m.parameters())
+    # without input gradients the result is the same (first-layer backward SpMM skipped)
+    m2 = _load(z, layers)
+    m2.train()
+    eng2 = ChromosomeEngine(m2, 2)
+    loss2 = torch.zeros(1, device=_dev())
+    eng2.run(g, eng2.pack(torch.from_numpy(z["x_f"]).to(_dev()), torch.from_numpy(z["x_r"]).to(_dev())), tgt, None, loss2,
+             train=True)
+    for (k, p), (_, q) in zip(m.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p.grad, q.grad), k
+
+
+def test_reference_sparse_tensor_is_accepted():
+    """The adjacency the reference's own process_graph returns (torch sparse COO) drops in."""
+    z = np.load(os.path.join(GOLDEN, "model_l2_stress.npz"))
+    m = _load(z, 2).eval()
+    coo = ogcn.coo_adjacency(z["indptr"], z["indices"]).to(_dev())
+    x = torch.from_numpy(z["x_f"]).to(_dev())
+    with torch.no_grad():
+        _, a, _, _ = m(x, coo, None)
+        _, b, _, _ = m(x, _graph(z), None)
+    assert torch.equal(a, b)
+    assert ogcn.max_rel(a.cpu(), torch.from_numpy(z["f32.eval.out_f"])) <= FWD_TOL
+    with pytest.raises(Exception):
+        m(x.cpu(), coo, None)                      # no CPU fallback
+
+
+def test_dropout_training_matches_oracle_with_injected_masks():
+    """Train mode with gcn_dropout 0.2: the oracle is fed the keep-masks the CUDA path drew."""
+    from chromegcn_b200 import ops
+    from chromegcn_b200.engine import ChromosomeEngine
+    z = np.load(os.path.join(GOLDEN, "model_l2_stress.npz"))
+    p = 0.2
+    m = _load(z, 2, dropout=p)
+    m.train()
+    g = _graph(z)
+    eng = ChromosomeEngine(m, 2)
+    x_f, x_r, tgt = (torch.from_numpy(z[k]) for k in ("x_f", "x_r", "target"))
+    n = x_f.shape[0]
+    probs = torch.empty(n, tgt.shape[1], device=_dev())
+    loss = torch.zeros(1, device=_dev())
+    out, _ = eng.run(g, eng.pack(x_f.to(_dev()), x_r.to(_dev())), tgt.to(_dev()), probs, loss, train=True)
+    seed, step = m._drop_seed, m._drop_step
+    mid = ops.dropout_mask(n, 2, 128, p, seed, step, 0).cpu()
+    head = ops.dropout_mask(n, 2, 128, p, seed, step, 1).cpu()
+    assert 0.15 < float((mid == 0).float().mean()) < 0.25
+    om = ogcn.ChromeGCNOracle(128, 128, tgt.shape[1], p, True, 2).double()
+    om.load_state_dict({k[4:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("sd0.")})
+    om.train()
+    adj = ogcn.coo_adjacency(z["indptr"], z["indices"], torch.float64)
+    lo, prob_o, pred_o, _ = ogcn.chromosome_step(om, x_f.double(), x_r.double(), tgt.double(), adj, None, True,
+                                                 masks_f=(mid[:, 0].double(), head[:, 0].double()),
+                                                 masks_r=(mid[:, 1].double(), head[:, 1].double()))
+    assert ogcn.max_rel(out.mean(1).cpu(), pred_o) <= FWD_TOL
+    assert abs(loss.item() - lo) <= FWD_TOL * abs(lo)
+    for (k, pp), (_, q) in zip(m.named_parameters(), om.named_parameters()):
+        err = ogcn.max_rel(pp.grad.cpu(), q.grad)
+        assert err <= 5e-5, (k, err)              # fp32 vs fp64 oracle, cancellation-prone sums included
+
+
+def test_large_graph_against_oracle():
+    """A config-1 sized chromosome (N = 20 000, 520 k stored entries): fused step vs the CPU oracle in fp64."""
+    from chromegcn_b200 import synthetic
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.engine import ChromosomeEngine
+    from chromegcn_b200.graph import HiCGraph
+    from oracle import adjacency as oadj
+    h = synthetic.make_hic("chr22")
+    ip, ix = oadj.build_adjacency_numpy(h.window_starts, h.bin1, h.bin2, h.val, h.norm, 1, 500000)
+    n = ip.shape[0] - 1
+    feats = synthetic.make_features("chr22", n)
+    torch.manual_seed(0)
+    om = ogcn.ChromeGCNOracle(128, 128, synthetic.NCLASS, 0.0, True, 2)
+    ogcn.stress_init_(om)
+    m = ChromeGCN(128, 128, synthetic.NCLASS, 0.0, True, 2)
+    m.load_state_dict(om.state_dict())
+    m = m.to(_dev()).train()
+    om = om.double().train()
+    adj = ogcn.coo_adjacency(ip, ix, torch.float64)
+    lo, prob_o, pred_o, _ = ogcn.chromosome_step(om, feats["forward"].double(), feats["backward"].double(),
+                                                 feats["target"].double(), adj, None, True)
+    g = HiCGraph.from_csr_pattern(ip, ix, _dev())
+    assert g.nnz == ip[-1] + n
+    eng = ChromosomeEngine(m, 2)
+    probs = torch.empty(n, synthetic.NCLASS, device=_dev())
+    loss = torch.zeros(1, device=_dev())
+    out, _ = eng.run(g, eng.pack(feats["forward"].to(_dev()), feats["backward"].to(_dev())), feats["target"].to(_dev()),
+                     probs, loss, train=True)
+    assert ogcn.max_rel(out.mean(1).cpu(), pred_o) <= FWD_TOL
+    assert ogcn.max_rel(probs.cpu(), prob_o) <= FWD_TOL
+    assert abs(loss.item() - lo) <= FWD_TOL * abs(lo)
+    for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
+        err = ogcn.max_rel(p.grad.cpu(), q.grad)
+        assert err <= 5e-5, (k, err)
+
+
+def _auc_aupr(targets, preds):
+    from sklearn import metrics as skm
+    aucs, auprs = [], []
+    for i in range(targets.shape[1]):
+        if targets[:, i].min() == targets[:, i].max():
+            continue
+        aucs.append(skm.roc_auc_score(targets[:, i], preds[:, i]))                     # utils/metrics.py:244
+        pr, rc, _ = skm.precision_recall_curve(targets[:, i], preds[:, i], pos_label=1)  # utils/metrics.py:172-173
+        auprs.append(skm.auc(rc, pr))
+    return np.array(aucs), np.array(auprs)
+
+
+@pytest.mark.parametrize("optim_kind", ["flat", "torch"])
+def test_finetune_matches_reference(tmp_path, optim_kind):
+    """Three epochs of finetune() (train on 2 chromosomes, validate on 1) against the reference's own
+    finetune.py run: losses, probabilities, per-label AUROC / AUPR, final state_dict."""
+    import argparse
+    import pickle
+    from scipy import sparse
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200 import finetune as ft
+    from chromegcn_b200.optim import get_optimizer
+    z = np.load(os.path.join(GOLDEN, "finetune.npz"))
+    nclass = int(z["nclass"])
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0.")}
+    m = ChromeGCN(128, 128, nclass, 0.0, True, 2)
+    m.load_state_dict(sd)
+    m = m.to(_dev())
+    graphs = {}
+    for c in ("chr1", "chr2", "chr3"):
+        ip, ix = z[c + ".indptr"], z[c + ".indices"]
+        n = ip.shape[0] - 1
+        graphs[c] = sparse.csr_matrix((np.ones(ix.shape[0]), ix, ip), shape=(n, n))
+    with open(tmp_path / "train_graphs_1200_SQRTVCnorm.pkl", "wb") as fp:
+        pickle.dump({c: graphs[c] for c in ("chr1", "chr2")}, fp)
+    with open(tmp_path / "valid_graphs_1200_SQRTVCnorm.pkl", "wb") as fp:
+        pickle.dump({"chr3": graphs["chr3"]}, fp)
+    opt = argparse.Namespace(adj_type="hic", graph_root=str(tmp_path), hicsize="1200", hicnorm="SQRTVC", optim="sgd", lr=0.25)
+    optimizer = (get_optimizer(m, opt) if optim_kind == "flat"
+                 else torch.optim.SGD(m.parameters(), lr=0.25, weight_decay=1e-6, momentum=0.9))
+    feats = lambda cs: {c: {k: torch.from_numpy(z["%s.%s" % (c, k)]) for k in ("forward", "backward", "target")} for c in cs}
+    train_d, valid_d = feats(["chr1", "chr2"]), feats(["chr3"])
+    ft.clear_caches()
+    for epoch in (1, 2, 3):
+        p, t, l = ft.finetune(None, m, train_d, None, optimizer, epoch, None, opt, "train")
+        pv, tv, lv = ft.finetune(None, m, valid_d, None, optimizer, epoch, None, opt, "valid")
+        assert not p.is_cuda and p.shape == (t.shape[0], nclass)
+        assert abs(l - float(z["epoch%d.train_loss" % epoch])) <= 2e-5 * abs(l)
+        assert abs(lv - float(z["epoch%d.valid_loss" % epoch])) <= 2e-5 * abs(lv)
+        gp, gpv = z["epoch%d.train_preds" % epoch], z["epoch%d.valid_preds" % epoch]
+        assert ogcn.max_rel(p, torch.from_numpy(gp)) <= 2e-5, epoch      # 6 SGD steps at lr 0.25 amplify rounding
+        assert ogcn.max_rel(pv, torch.from_numpy(gpv)) <= 2e-5, epoch
+        for ours, ref, targ in ((p.numpy(), gp, t.numpy()), (pv.numpy(), gpv, tv.numpy())):
+            a1, r1 = _auc_aupr(targ, ours)
+            a2, r2 = _auc_aupr(targ, ref)
+            assert np.abs(a1 - a2).max() <= 1e-4 and np.abs(r1 - r2).max() <= 1e-4
+    for k, v in m.state_dict().items():
+        assert ogcn.max_rel(v.float().cpu(), torch.from_numpy(z["sd3." + k]).float()) <= 5e-5, k

@@ -1,0 +1,84 @@
+"""CPU: the C-ABI library loads, exports every symbol include/chromegcn.h declares, the ctypes
+structs match the C layout, and the product path refuses to run without a GPU (no fallback)."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from chromegcn_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def _declared():
+    hdr = open(os.path.join(REPO, "include", "chromegcn.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgcn_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from chromegcn_b200 import _lib
+    names = _declared()
+    assert len(names) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (cgcn_[a-z0-9_]+)", out))
+    assert set(names) <= exported, sorted(set(names) - exported)
+    assert set(names) == set(_lib.PROTOTYPES), sorted(set(names) ^ set(_lib.PROTOTYPES))
+    assert not re.search(r"torch|at::|c10::", out)            # plain C ABI, no torch types behind it
+
+
+def test_abi_version_and_struct_layout(lib):
+    import ctypes as C
+    from chromegcn_b200 import _lib
+    assert lib.cgcn_abi_version() == 1
+    assert lib.cgcn_sizeof(0) == C.sizeof(_lib.Graph)
+    assert lib.cgcn_sizeof(1) == C.sizeof(_lib.Params)
+    assert lib.cgcn_sizeof(2) == C.sizeof(_lib.Model)
+
+
+def test_sass_is_sm100a(lib):
+    from chromegcn_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(lib):
+    from chromegcn_b200 import _lib, ops
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.graph import process_graph
+    m = ChromeGCN(128, 128, 7, 0.2, True, 2)
+    assert sorted(k for k, _ in m.named_parameters()) == sorted(
+        ["GC1.weight", "GC1.bias", "W1.weight", "W1.bias", "GC2.weight", "GC2.bias", "W2.weight", "W2.bias",
+         "batch_norm.weight", "batch_norm.bias", "out.weight", "out.bias"])
+    with pytest.raises(_lib.ChromeGCNNativeError):
+        m(torch.randn(4, 128), None, None)
+    with pytest.raises(_lib.ChromeGCNNativeError):
+        process_graph("none", None, 4, "chr1")
+    with pytest.raises(_lib.ChromeGCNNativeError):
+        ops.dropout_mask(4, 1, 128, 0.1, 1, 1, 0)
+
+
+def test_reference_state_dict_loads():
+    """Checkpoints interchange: the oracle / reference state_dict loads into the drop-in module."""
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from oracle.gcn import ChromeGCNOracle
+    for layers in (1, 2, 3):
+        ref = ChromeGCNOracle(128, 128, 11, 0.2, True, layers)
+        ours = ChromeGCN(128, 128, 11, 0.2, True, layers)
+        res = ours.load_state_dict(ref.state_dict())
+        assert not res.missing_keys and not res.unexpected_keys
+        assert ours.num_layers == (2 if layers == 2 else 1)       # reference quirk: layers != 2 -> one layer
+        assert [tuple(v.shape) for v in ours.state_dict().values()] == [tuple(v.shape) for v in ref.state_dict().values()]
+    # reference initialisation: xavier_normal_(gain=0.02), zero bias (models/SubLayers.py:32-35)
+    torch.manual_seed(0)
+    m = ChromeGCN(128, 128, 11, 0.2, True, 2)
+    assert float(m.GC1.bias.abs().max()) == 0.0
+    assert abs(float(m.GC1.weight.std()) - 0.02 * (2.0 / 256) ** 0.5) < 2e-4
