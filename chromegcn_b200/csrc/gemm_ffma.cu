@@ -195,7 +195,7 @@ int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transp
 }
 
 // -------------------------------------------------------------------------------- gram
-constexpr int GRAM_MIN_ROWS = 2048;   // rows per CTA (lower bound): bounds fp32 accumulation length
+constexpr int GRAM_MIN_ROWS = 256;    // rows per CTA (lower bound); the upper bound 4*SMs CTAs caps the partial tiles
 
 struct GramArgs {
   const float* A;

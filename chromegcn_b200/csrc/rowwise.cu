@@ -45,6 +45,36 @@ __device__ __forceinline__ void block_combine(float* red, int K, float* __restri
   }
 }
 
+
+// Fixed-order parallel reduction of per-CTA partials: a CTA of (32 columns) x (FIN_SLICES slices of the
+// parts axis); every thread sums its slice in fp64, slices are combined in slice order in shared memory.
+constexpr int FIN_SLICES = 16;
+
+template <int NV>
+__device__ __forceinline__ void reduce_parts(const float* __restrict__ partial, int parts, size_t stride,
+                                             const int (&offs)[NV], bool active, double (&out)[NV]) {
+  __shared__ double sh[FIN_SLICES][32][NV];
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  if (active) {
+    for (int q = threadIdx.y; q < parts; q += FIN_SLICES) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] += static_cast<double>(partial[static_cast<size_t>(q) * stride + offs[v]]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) sh[threadIdx.y][threadIdx.x][v] = acc[v];
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double t = 0.0;
+    if (threadIdx.y == 0)
+      for (int y = 0; y < FIN_SLICES; ++y) t += sh[y][threadIdx.x][v];
+    out[v] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------- gate forward
 
 template <int DV, int S, bool STATS>
@@ -114,31 +144,39 @@ __global__ void __launch_bounds__(RW_THREADS) gate_fwd_kernel(const GateFwdArgs 
 // BatchNorm1d statistics (models/ChromeModels.py:49): per strand call, batch mean / biased variance
 // over the n rows; running stats updated once per strand, in strand order, with the unbiased
 // variance (torch.nn.BatchNorm1d semantics).  Eval mode: running stats.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int parts, int n, int S, int D, float eps,
-                                   float momentum, int training, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, int64_t* __restrict__ num_batches,
-                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
+template <int S>
+__global__ void __launch_bounds__(32 * FIN_SLICES)
+bn_finalize_kernel(const float* __restrict__ partial, int parts, int n, int D, float eps, float momentum, int training,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ num_batches,
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool active = c < D;
   const int K = 2 * S * D;
   if (!training) {
-    const float m = running_mean[c];
-    const float r = static_cast<float>(1.0 / sqrt(static_cast<double>(running_var[c]) + static_cast<double>(eps)));
-    for (int s = 0; s < S; ++s) {
-      mean_out[s * D + c] = m;
-      rstd_out[s * D + c] = r;
+    if (active && threadIdx.y == 0) {
+      const float m = running_mean[c];
+      const float r = static_cast<float>(1.0 / sqrt(static_cast<double>(running_var[c]) + static_cast<double>(eps)));
+      for (int s = 0; s < S; ++s) {
+        mean_out[s * D + c] = m;
+        rstd_out[s * D + c] = r;
+      }
     }
     return;
   }
-  float rm = running_mean[c], rv = running_var[c];
+  int offs[2 * S];
+#pragma unroll
   for (int s = 0; s < S; ++s) {
-    double sum = 0.0, sq = 0.0;
-    for (int q = 0; q < parts; ++q) {
-      sum += static_cast<double>(partial[static_cast<size_t>(q) * K + (0 * S + s) * D + c]);
-      sq += static_cast<double>(partial[static_cast<size_t>(q) * K + (1 * S + s) * D + c]);
-    }
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;
+    offs[2 * s] = (0 * S + s) * D + c;
+    offs[2 * s + 1] = (1 * S + s) * D + c;
+  }
+  double sums[2 * S];
+  reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
+  if (!active || threadIdx.y != 0) return;
+  float rm = running_mean[c], rv = running_var[c];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const double mean = sums[2 * s] / n;
+    double var = sums[2 * s + 1] / n - mean * mean;
     if (var < 0.0) var = 0.0;
     mean_out[s * D + c] = static_cast<float>(mean);
     rstd_out[s * D + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -217,23 +255,29 @@ __global__ void __launch_bounds__(RW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
 
 // c1 = mean(dbn), c2 = mean(dbn * xhat) per strand (zero in eval mode: running stats are constants);
 // d gamma = sum_s sum dbn*xhat ; d beta = sum_s sum dbn.
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int n, int S, int D, int training,
-                                       float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
+template <int S>
+__global__ void __launch_bounds__(32 * FIN_SLICES)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int n, int D, int training, float* __restrict__ c1,
+                       float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool active = c < D;
   const int K = 2 * S * D;
-  double tg = 0.0, tb = 0.0;
+  int offs[2 * S];
+#pragma unroll
   for (int s = 0; s < S; ++s) {
-    double a1 = 0.0, a2 = 0.0;
-    for (int q = 0; q < parts; ++q) {
-      a1 += static_cast<double>(partial[static_cast<size_t>(q) * K + (0 * S + s) * D + c]);
-      a2 += static_cast<double>(partial[static_cast<size_t>(q) * K + (1 * S + s) * D + c]);
-    }
-    c1[s * D + c] = training ? static_cast<float>(a1 / n) : 0.f;
-    c2[s * D + c] = training ? static_cast<float>(a2 / n) : 0.f;
-    tb += a1;
-    tg += a2;
+    offs[2 * s] = (0 * S + s) * D + c;
+    offs[2 * s + 1] = (1 * S + s) * D + c;
+  }
+  double sums[2 * S];
+  reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
+  if (!active || threadIdx.y != 0) return;
+  double tg = 0.0, tb = 0.0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    c1[s * D + c] = training ? static_cast<float>(sums[2 * s] / n) : 0.f;
+    c2[s * D + c] = training ? static_cast<float>(sums[2 * s + 1] / n) : 0.f;
+    tb += sums[2 * s];
+    tg += sums[2 * s + 1];
   }
   dgamma[c] = static_cast<float>(tg);
   dbeta[c] = static_cast<float>(tb);
@@ -320,15 +364,22 @@ struct ColFinalizeArgs {
   int begin[3], len[3];
 };
 
-__global__ void col_finalize_kernel(const ColFinalizeArgs a) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * FIN_SLICES) col_finalize_kernel(const ColFinalizeArgs a) {
+  const int t = blockIdx.x * 32 + threadIdx.x;        // index into the concatenation of the segments
+  int q = -1, local = 0, base = 0;
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    if (a.dst[q] == nullptr || t >= a.len[q]) continue;
-    double s = 0.0;
-    for (int p = 0; p < a.parts; ++p) s += static_cast<double>(a.partial[static_cast<size_t>(p) * a.stride + a.begin[q] + t]);
-    a.dst[q][t] = static_cast<float>(s);
+  for (int i = 0; i < 3; ++i) {
+    if (q < 0 && a.dst[i] != nullptr && t >= base && t < base + a.len[i]) {
+      q = i;
+      local = t - base;
+    }
+    if (a.dst[i] != nullptr) base += a.len[i];
   }
+  const bool active = q >= 0;
+  int offs[1] = {active ? a.begin[q] + local : 0};
+  double out[1];
+  reduce_parts<1>(a.partial, a.parts, a.stride, offs, active, out);
+  if (active && threadIdx.y == 0) a.dst[q][local] = static_cast<float>(out[0]);
 }
 
 // ------------------------------------------------------------------------------ generic column sum
@@ -394,11 +445,17 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
   }
 }
 
-__global__ void bce_finalize_kernel(const float* __restrict__ partial, int parts, float inv_count, float* loss_sum) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int p = 0; p < parts; ++p) s += static_cast<double>(partial[p]);
-    *loss_sum += static_cast<float>(s * static_cast<double>(inv_count));
+__global__ void __launch_bounds__(256) bce_finalize_kernel(const float* __restrict__ partial, int parts, float inv_count,
+                                                            float* loss_sum) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int p = threadIdx.x; p < parts; p += 256) s += static_cast<double>(partial[p]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 256; ++i) t += sh[i];
+    *loss_sum += static_cast<float>(t * static_cast<double>(inv_count));
   }
 }
 
@@ -505,8 +562,13 @@ int gate_fwd_launch(const GateFwdArgs& a, int d, int S, bool stats, int* grid_ou
 int bn_finalize_launch(const float* partial, int parts, int n, int S, int D, float eps, float momentum, int training,
                        float* running_mean, float* running_var, int64_t* nbt, float* mean_out, float* rstd_out,
                        cudaStream_t stream) {
-  bn_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, parts, n, S, D, eps, momentum, training, running_mean,
-                                                          running_var, nbt, mean_out, rstd_out);
+  const dim3 blk(32, FIN_SLICES);
+  if (S == 1)
+    bn_finalize_kernel<1><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, eps, momentum, training, running_mean,
+                                                             running_var, nbt, mean_out, rstd_out);
+  else
+    bn_finalize_kernel<2><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, eps, momentum, training, running_mean,
+                                                             running_var, nbt, mean_out, rstd_out);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -530,7 +592,11 @@ int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, 
 
 int bn_bwd_finalize_launch(const float* partial, int parts, int n, int S, int D, int training, float* c1, float* c2,
                            float* dgamma, float* dbeta, cudaStream_t stream) {
-  bn_bwd_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, parts, n, S, D, training, c1, c2, dgamma, dbeta);
+  const dim3 blk(32, FIN_SLICES);
+  if (S == 1)
+    bn_bwd_finalize_kernel<1><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, training, c1, c2, dgamma, dbeta);
+  else
+    bn_bwd_finalize_kernel<2><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, training, c1, c2, dgamma, dbeta);
   return check_launch("bn_bwd_finalize_kernel");
 }
 
@@ -558,7 +624,7 @@ int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, float* db, fl
   f.dst[0] = db;  f.begin[0] = 0;      f.len[0] = d;
   f.dst[1] = dwg; f.begin[1] = d;      f.len[1] = d;
   f.dst[2] = dbg; f.begin[2] = 2 * d;  f.len[2] = 1;
-  col_finalize_kernel<<<(d + 127) / 128, 128, 0, stream>>>(f);
+  col_finalize_kernel<<<(2 * d + 1 + 31) / 32, dim3(32, FIN_SLICES), 0, stream>>>(f);
   return check_launch("col_finalize_kernel");
 }
 
@@ -580,7 +646,7 @@ int colsum_launch(const float* X, int64_t rows, int cols, float* dst, float* par
   f.parts = parts;
   f.stride = 128;
   f.dst[0] = dst; f.begin[0] = 0; f.len[0] = cols;
-  col_finalize_kernel<<<1, 128, 0, stream>>>(f);
+  col_finalize_kernel<<<(cols + 31) / 32, dim3(32, FIN_SLICES), 0, stream>>>(f);
   return check_launch("col_finalize_kernel");
 }
 
@@ -595,7 +661,7 @@ int bce_launch(const float* out, const float* target, int n, int C, int S, float
   if (grid < 1) grid = 1;
   bce_kernel<<<grid, 256, 0, stream>>>(a);
   CGCN_TRY(check_launch("bce_kernel"));
-  bce_finalize_kernel<<<1, 32, 0, stream>>>(partial, grid, a.inv_count, loss_sum);
+  bce_finalize_kernel<<<1, 256, 0, stream>>>(partial, grid, a.inv_count, loss_sum);
   return check_launch("bce_finalize_kernel");
 }
 
