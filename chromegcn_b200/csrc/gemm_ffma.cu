@@ -305,6 +305,11 @@ __global__ void gram_finalize_kernel(const float* __restrict__ partial, int part
   *dst = accumulate ? static_cast<float>(static_cast<double>(*dst) + s) : static_cast<float>(s);
 }
 
+void gram_finalize_launch(const float* partial, int parts, int count, float* C, int nb, int64_t ldc, int accumulate,
+                          cudaStream_t stream) {
+  gram_finalize_kernel<<<(count + 255) / 256, 256, 0, stream>>>(partial, parts, count, C, nb, ldc, accumulate);
+}
+
 int64_t gram_rows_per_cta(int64_t m) {
   const int64_t target = (m + 4LL * sm_count() - 1) / (4LL * sm_count());
   int64_t rows = target > GRAM_MIN_ROWS ? target : GRAM_MIN_ROWS;

@@ -1,22 +1,548 @@
-// tcgen05 (3xTF32) dense contractions -- placeholder until the tensor-core kernels land:
-// reports "unsupported" so every contraction runs on the fp32 FFMA kernels of gemm_ffma.cu.
+// tcgen05 / TMEM dense contractions for the GCN path (sm_100a), fp32-faithful via 3xTF32.
+//
+// The two contraction shapes of the model (see gemm_ffma.cu) on the 5th-generation tensor cores:
+//
+//   row panel  C[m x 128] = rowscale * (A[m x 128] * Bw) + bias       (A_hat x) W ,  G W^T
+//   gram       C[128x128] = sum_r A[r,:]^T (x) B[r,:]                 weight gradients X^T G
+//
+// fp32 parity (<= 1e-5) rules out a single TF32 pass (8.8e-5).  Every fp32 operand v is
+// split in registers into hi = v & 0xffffe000 (exactly a TF32 number) and lo = v - hi (exact in fp32,
+// then truncated to TF32), and each tile accumulates hi*hi + lo*hi + hi*lo in the fp32 TMEM
+// accumulator: three kind::tf32 MMAs per k-step.  Because the split needs the operands in registers
+// anyway, tiles are staged global -> registers -> shared memory by producer warps that write the
+// UMMA canonical SWIZZLE_128B layout directly (no TMA descriptor): 16-byte chunk c of 128-byte row r
+// lands at  (r/8)*1024 + (r%8)*128 + ((c ^ (r%8)) * 16).
+//
+// Warp roles (416 threads, one CTA per SM, persistent over tiles):
+//   warps 0-3   epilogue: tcgen05.ld the accumulator (lane = tile row), scale/bias, 128-bit stores
+//   warp  4     TMEM alloc/dealloc + the single-thread tcgen05.mma issuer
+//   warps 5-12  producers: coalesced 128-bit global loads, hi/lo split, swizzled st.shared,
+//               fence.proxy.async, mbarrier arrive
+// Pipelines: smem stage full/empty mbarriers (producers <-> MMA, freed by tcgen05.commit) and, in
+// the row-panel kernel, a double-buffered TMEM accumulator (MMA <-> epilogue).
 #include "common.cuh"
 
 namespace cgcn {
 
-bool tc_rowpanel_supported(int64_t, int64_t, int, int, const void*, const void*) { return false; }
-bool tc_gram_supported(int64_t, int64_t, int, int, const void*, const void*) { return false; }
-size_t tc_workspace_bytes() { return 256; }
+void gram_finalize_launch(const float* partial, int parts, int count, float* C, int nb, int64_t ldc, int accumulate,
+                          cudaStream_t stream);
+int64_t gram_rows_per_cta(int64_t m);
+size_t gram_workspace_bytes(int64_t m);
 
-int gemm_rowpanel_tc(const float*, int64_t, const float*, int, const float*, float*, int64_t, int64_t, int, int,
-                     const int32_t*, int, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 row-panel GEMM not built");
-  return CGCN_ERR_INVALID;
+namespace tc {
+
+constexpr int TILE = 128;
+constexpr int KCH = 32;                               // floats per 128-byte swizzle row
+constexpr int ATOM_BYTES = 1024;                      // 8 rows x 128 B
+constexpr int CHUNK_BYTES = TILE * KCH * 4;           // 128 rows x 128 B = 16 KB
+constexpr int STAGES = 3;
+constexpr int NUM_EPI_WARPS = 4, NUM_PROD_WARPS = 8;
+constexpr int MMA_WARP = NUM_EPI_WARPS;
+constexpr int THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;      // 416
+constexpr int PROD_THREADS = NUM_PROD_WARPS * 32;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-int gemm_gram_tc(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int, int, int, void*, size_t,
-                 cudaStream_t) {
-  set_error("tcgen05 gram GEMM not built");
-  return CGCN_ERR_INVALID;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, M = N = 128, K = 8
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, version 1): start address, leading / stride byte
+// offsets in 16-byte units.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2 /* SWIZZLE_128B */) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;      // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(layout_type) << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+// Instruction descriptor: D = F32, A = B = TF32, M = N = 128; bit 15 / 16 = A / B MN-major.
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((128u >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xFFFFE000u;
+  lo = __float_as_uint(v - __uint_as_float(hi)) & 0xFFFFE000u;
+}
+__device__ __forceinline__ void split4(const float4 v, uint4& hi, uint4& lo) {
+  split_tf32(v.x, hi.x, lo.x);
+  split_tf32(v.y, hi.y, lo.y);
+  split_tf32(v.z, hi.z, lo.z);
+  split_tf32(v.w, hi.w, lo.w);
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------ B image (weights) preparation
+// img[(hi|lo)][kchunk 4][n 128][32 floats] in the K-major SWIZZLE_128B layout; Bw(n,k) is the weight
+// that multiplies A[:,k] into C[:,n].
+__global__ void tc_prep_b_kernel(const float* __restrict__ B, int b_transposed, uint32_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= TILE * TILE) return;
+  const int n = idx >> 7, k = idx & 127;
+  const float v = b_transposed ? __ldg(B + n * TILE + k) : __ldg(B + k * TILE + n);
+  uint32_t hi, lo;
+  split_tf32(v, hi, lo);
+  const int kc = k >> 5, kk = k & 31;
+  const int off = (kc * CHUNK_BYTES + (n >> 3) * ATOM_BYTES + (n & 7) * 128 + (((kk >> 2) ^ (n & 7)) << 4) + (kk & 3) * 4) >> 2;
+  img[off] = hi;
+  img[(4 * CHUNK_BYTES >> 2) + off] = lo;
+}
+
+// ------------------------------------------------------------------ row-panel kernel
+struct RowPanelTcArgs {
+  const float* A;
+  int64_t lda;
+  const uint32_t* b_img;       // 128 KB prepared image
+  const float* bias;
+  float* C;
+  int64_t ldc;
+  int64_t m;
+  const int32_t* rowscale_rowptr;
+  int rowscale_group;
+};
+
+constexpr int RP_B_BYTES = 2 * 4 * CHUNK_BYTES;                 // hi + lo, 4 k-chunks: 128 KB
+constexpr int RP_STAGE_BYTES = 2 * CHUNK_BYTES;                 // A hi + lo of one k-chunk: 32 KB
+constexpr int RP_SMEM = RP_B_BYTES + STAGES * RP_STAGE_BYTES + 256 + 1024;
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowPanelTcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = base;
+  const uint32_t sA = base + RP_B_BYTES;
+  const uint32_t sBar = sA + STAGES * RP_STAGE_BYTES;           // full[3] empty[3] tfull[2] tempty[2] | tmem ptr
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tfull = sBar + 16 * STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t s_tmem_ptr = bar_tempty + 16;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));        // generic pointer to the aligned base
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tiles = (p.m + TILE - 1) / TILE;
+
+  // B image: global -> smem (already swizzled), all threads
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.b_img);
+    constexpr int N16 = RP_B_BYTES / 16;                        // 8192 x 16 B, batches of 8 loads in flight
+    for (int i0 = threadIdx.x; i0 < N16; i0 += THREADS * 8) {
+      uint4 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * THREADS;
+        t[j] = i < N16 ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * THREADS;
+        if (i < N16) sts128(sB + i * 16, t[j]);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, NUM_PROD_WARPS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(s_tmem_ptr, 256);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (s_tmem_ptr - base));
+
+  if (warp > MMA_WARP) {
+    // ===================== producers =====================
+    const int pt = threadIdx.x - (MMA_WARP + 1) * 32;           // 0..255
+    uint32_t stage = 0, phase = 0;
+    // register ring: one whole tile (4 k-chunks x 4 float4) of look-ahead per thread = 64 KB in flight per SM
+    float4 v[4][4];
+    auto issue = [&](int64_t tile, int kc) {
+      const int64_t row0 = tile * TILE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = pt + PROD_THREADS * i;
+        const int r = u >> 3, c = u & 7;
+        const int64_t grow = row0 + r;
+        v[kc][i] = (tile < tiles && grow < p.m) ? ldg4(p.A + grow * p.lda + kc * KCH + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) issue(blockIdx.x, kc);
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t sHi = sA + stage * RP_STAGE_BYTES, sLo = sHi + CHUNK_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = pt + PROD_THREADS * i;
+          const int r = u >> 3, c = u & 7;
+          const uint32_t off = (r >> 3) * ATOM_BYTES + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+          uint4 hi, lo;
+          split4(v[kc][i], hi, lo);
+          sts128(sHi + off, hi);
+          sts128(sLo + off, lo);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        issue(tile + gridDim.x, kc);                            // refill this slot for the next tile
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(false, false);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * TILE;
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t aHi = sA + stage * RP_STAGE_BYTES, aLo = aHi + CHUNK_BYTES;
+          const uint32_t bHi = sB + kc * CHUNK_BYTES, bLo = bHi + 4 * CHUNK_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t dah = make_desc(aHi + ks * 32, 16, ATOM_BYTES), dal = make_desc(aLo + ks * 32, 16, ATOM_BYTES);
+            const uint64_t dbh = make_desc(bHi + ks * 32, 16, ATOM_BYTES), dbl = make_desc(bLo + ks * 32, 16, ATOM_BYTES);
+            umma_tf32(d_tmem, dal, dbh, idesc, (kc | ks) != 0);      // small terms first
+            umma_tf32(d_tmem, dah, dbl, idesc, 1);
+            umma_tf32(d_tmem, dah, dbh, idesc, 1);
+          }
+          umma_commit(bar_empty + 8 * stage);                     // frees the stage when these MMAs retire
+          if (kc == 3) umma_commit(bar_tfull + 8 * acc);          // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t grow = tile * TILE + warp * 32 + lane;
+      float scale = 1.0f;
+      if (p.rowscale_rowptr != nullptr && grow < p.m)
+        scale = inv_degree(p.rowscale_rowptr, static_cast<int>(grow / p.rowscale_group));
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * TILE + cc * 32, r);
+        if (grow < p.m) {
+          float* dst = p.C + grow * p.ldc + cc * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(r[4 * j]) * scale, __uint_as_float(r[4 * j + 1]) * scale,
+                                   __uint_as_float(r[4 * j + 2]) * scale, __uint_as_float(r[4 * j + 3]) * scale);
+            if (p.bias != nullptr) {
+              const float4 b = ldg4(p.bias + cc * 32 + 4 * j);
+              o.x += b.x;
+              o.y += b.y;
+              o.z += b.z;
+              o.w += b.w;
+            }
+            st4(dst + 4 * j, o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------ gram kernel
+struct GramTcArgs {
+  const float* A;
+  int64_t lda;
+  const float* B;
+  int64_t ldb;
+  int64_t m;
+  int64_t rows_per_cta;        // multiple of 32
+  float* partial;              // [gridDim.x][128][128]
+};
+
+constexpr int GR_OP_BYTES = 2 * CHUNK_BYTES;                     // one operand, hi + lo, 32 rows x 128 cols: 32 KB
+constexpr int GR_STAGE_BYTES = 2 * GR_OP_BYTES;                  // A + B: 64 KB
+constexpr int GR_SMEM = STAGES * GR_STAGE_BYTES + 256 + 1024;
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sS = base;
+  const uint32_t sBar = base + STAGES * GR_STAGE_BYTES;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tfull = sBar + 16 * STAGES;
+  const uint32_t s_tmem_ptr = bar_tfull + 8;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.x) * p.rows_per_cta;
+  const int64_t r_end = min(r_begin + p.rows_per_cta, p.m);
+  const int chunks = static_cast<int>((r_end - r_begin + KCH - 1) / KCH);       // >= 1 by construction
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, NUM_PROD_WARPS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(s_tmem_ptr, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (s_tmem_ptr - base));
+
+  if (warp > MMA_WARP) {
+    // producers: 32 rows x 128 floats of A and of B per stage; one warp moves one 512-byte row per
+    // instruction.  MN-major 32-bit operands must use SWIZZLE_128B_BASE32B (the only MN-major layout
+    // kind::tf32 accepts): 128-byte rows (32 MN elements of one k), atoms of 4 k-rows, 32-byte chunks
+    // XOR-ed with (k % 4).  16-byte chunk c (floats 4c..4c+3) of row r goes to
+    // (c/8)*4096 + r*128 + ((((c%8)/2) ^ (r%4)) * 32) + (c%2)*16      [LBO = 4096, SBO = 512].
+    const int pt = threadIdx.x - (MMA_WARP + 1) * 32;
+    uint32_t stage = 0, phase = 0;
+    // two chunks of look-ahead in registers (2 x 8 float4 per thread = 64 KB in flight per SM)
+    float4 va[2][4], vb[2][4];
+    auto issue = [&](int ch, int slot) {
+      const int64_t row0 = r_begin + static_cast<int64_t>(ch) * KCH;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = pt + PROD_THREADS * i;
+        const int r = u >> 5, c = u & 31;
+        const int64_t grow = row0 + r;
+        const bool ok = ch < chunks && grow < r_end;
+        va[slot][i] = ok ? ldg4(p.A + grow * p.lda + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[slot][i] = ok ? ldg4(p.B + grow * p.ldb + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    issue(0, 0);
+    issue(1, 1);
+    for (int ch0 = 0; ch0 < chunks; ch0 += 2) {
+#pragma unroll
+      for (int slot = 0; slot < 2; ++slot) {
+        const int ch = ch0 + slot;
+        if (ch >= chunks) break;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t sAh = sS + stage * GR_STAGE_BYTES, sAl = sAh + CHUNK_BYTES;
+        const uint32_t sBh = sAh + GR_OP_BYTES, sBl = sBh + CHUNK_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = pt + PROD_THREADS * i;
+          const int r = u >> 5, c = u & 31;
+          const uint32_t off = (c >> 3) * 4096 + r * 128 + ((((c & 7) >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4);
+          uint4 hi, lo;
+          split4(va[slot][i], hi, lo);
+          sts128(sAh + off, hi);
+          sts128(sAl + off, lo);
+          split4(vb[slot][i], hi, lo);
+          sts128(sBh + off, hi);
+          sts128(sBl + off, lo);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        issue(ch + 2, slot);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    constexpr uint32_t idesc = make_idesc(true, true);
+    uint32_t stage = 0, phase = 0;
+    for (int ch = 0; ch < chunks; ++ch) {
+      mbar_wait(bar_full + 8 * stage, phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t aHi = sS + stage * GR_STAGE_BYTES, aLo = aHi + CHUNK_BYTES;
+        const uint32_t bHi = aHi + GR_OP_BYTES, bLo = bHi + CHUNK_BYTES;
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {
+          const uint64_t dah = make_desc(aHi + kg * 1024, 4096, 512, 1), dal = make_desc(aLo + kg * 1024, 4096, 512, 1);
+          const uint64_t dbh = make_desc(bHi + kg * 1024, 4096, 512, 1), dbl = make_desc(bLo + kg * 1024, 4096, 512, 1);
+          umma_tf32(tmem_base, dal, dbh, idesc, (ch | kg) != 0);
+          umma_tf32(tmem_base, dah, dbl, idesc, 1);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1);
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (ch == chunks - 1) umma_commit(bar_tfull);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    mbar_wait(bar_tfull, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;                            // row of C = column of A
+    float* dst = p.partial + static_cast<size_t>(blockIdx.x) * TILE * TILE + row * TILE;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cc * 32, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        st4(dst + cc * 32 + 4 * j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------ host side
+static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+bool tc_rowpanel_supported(int64_t lda, int64_t ldc, int n, int k, const void* A, const void* C) {
+  return n == 128 && k == 128 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(C);
+}
+bool tc_gram_supported(int64_t lda, int64_t ldb, int ka, int nb, const void* A, const void* B) {
+  return ka == 128 && nb == 128 && lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B);
+}
+size_t tc_workspace_bytes() { return tc::RP_B_BYTES + 256; }
+
+int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
+                     int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  CGCN_REQUIRE(A && B && C, "cgcn_gemm_rowpanel: null operand");
+  CGCN_REQUIRE(tc_rowpanel_supported(lda, ldc, n, k, A, C), "cgcn_gemm_rowpanel(tcgen05): needs n = k = 128 and 16-byte aligned rows");
+  CGCN_REQUIRE(bias == nullptr || aligned16(bias), "cgcn_gemm_rowpanel(tcgen05): bias must be 16-byte aligned");
+  if (workspace == nullptr || workspace_bytes < tc_workspace_bytes() || !aligned16(workspace)) {
+    set_error("cgcn_gemm_rowpanel(tcgen05): needs a %zu-byte, 16-byte aligned workspace", tc_workspace_bytes());
+    return CGCN_ERR_WORKSPACE;
+  }
+  if (m <= 0) return CGCN_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_rowpanel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::RP_SMEM));
+    attr_set = true;
+  }
+  uint32_t* img = static_cast<uint32_t*>(workspace);
+  tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, img);
+  CGCN_TRY(check_launch("tc_prep_b_kernel"));
+  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rowscale_rowptr, rowscale_group};
+  const int64_t tiles = (m + tc::TILE - 1) / tc::TILE;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  tc::gemm_rowpanel_tc_kernel<<<grid, tc::THREADS, tc::RP_SMEM, stream>>>(p);
+  return check_launch("gemm_rowpanel_tc_kernel");
+}
+
+int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
+                 int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  CGCN_REQUIRE(A && B && C && m >= 1, "cgcn_gemm_gram: bad operand");
+  CGCN_REQUIRE(tc_gram_supported(lda, ldb, ka, nb, A, B), "cgcn_gemm_gram(tcgen05): needs ka = nb = 128 and 16-byte aligned rows");
+  if (workspace == nullptr || workspace_bytes < gram_workspace_bytes(m) || !aligned16(workspace)) {
+    set_error("cgcn_gemm_gram(tcgen05): workspace %zu < %zu bytes", workspace_bytes, gram_workspace_bytes(m));
+    return CGCN_ERR_WORKSPACE;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GR_SMEM));
+    attr_set = true;
+  }
+  int64_t rows = gram_rows_per_cta(m);
+  rows = (rows + tc::KCH - 1) / tc::KCH * tc::KCH;
+  const int parts = static_cast<int>((m + rows - 1) / rows);
+  tc::GramTcArgs p{A, lda, B, ldb, m, rows, static_cast<float*>(workspace)};
+  tc::gemm_gram_tc_kernel<<<parts, tc::THREADS, tc::GR_SMEM, stream>>>(p);
+  CGCN_TRY(check_launch("gemm_gram_tc_kernel"));
+  gram_finalize_launch(p.partial, parts, 128 * 128, C, 128, ldc, accumulate, stream);
+  return check_launch("gram_finalize_kernel");
 }
 
 }  // namespace cgcn
