@@ -32,7 +32,7 @@ class Model(C.Structure):
     _fields_ = [("graph", Graph),
                 ("d", C.c_int32), ("nclass", C.c_int32), ("layers", C.c_int32), ("strands", C.c_int32),
                 ("training", C.c_int32), ("gemm_impl", C.c_int32), ("need_input_grad", C.c_int32),
-                ("reserved0", C.c_int32),
+                ("out_ld", C.c_int32),
                 ("dropout_p", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("reserved1", C.c_float),
                 ("seed", C.c_uint64), ("step", C.c_uint64),
                 ("params", Params), ("grads", Params),
@@ -67,7 +67,7 @@ PROTOTYPES = {
     "cgcn_model_forward": (C.c_int, [C.POINTER(Model)]),
     "cgcn_model_backward": (C.c_int, [C.POINTER(Model)]),
     "cgcn_bce_workspace_bytes": (_SZ, [_I32, _I32]),
-    "cgcn_bce_loss": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "cgcn_bce_loss": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
     "cgcn_train_step": (C.c_int, [C.POINTER(Model), _P, _P, _P, _P]),
     "cgcn_sgd_step": (C.c_int, [_P, _P, _P, _I64, _F32, _F32, _F32, _F32, _P]),
     "cgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _I64, _F32, _P]),

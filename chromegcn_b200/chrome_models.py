@@ -23,6 +23,12 @@ PARAM_ORDER = ["GC1.weight", "GC1.bias", "W1.weight", "W1.bias", "GC2.weight", "
                "batch_norm.weight", "batch_norm.bias", "out.weight", "out.bias"]
 
 
+def padded_classes(nclass: int) -> int:
+    """Row pitch (floats) of the logit buffers: a multiple of 4 keeps rows 16-byte aligned, which puts the
+    head contractions on the tcgen05 path."""
+    return (nclass + 3) // 4 * 4
+
+
 def _as_graph(adj, cache: Dict) -> HiCGraph:
     if isinstance(adj, HiCGraph):
         return adj
@@ -124,8 +130,9 @@ def build_model_struct(graph: HiCGraph, d: int, nclass: int, layers: int, strand
                        running_mean: torch.Tensor, running_var: torch.Tensor, num_batches: Optional[torch.Tensor],
                        x_in: torch.Tensor, x_in_grad: Optional[torch.Tensor], out: torch.Tensor,
                        gates: List[Optional[torch.Tensor]], out_grad: Optional[torch.Tensor], workspace: torch.Tensor,
-                       gemm_impl: int = 0, bn_momentum: float = 0.1, bn_eps: float = 1e-5) -> _lib.Model:
+                       gemm_impl: int = 0, bn_momentum: float = 0.1, bn_eps: float = 1e-5, out_ld: int = 0) -> _lib.Model:
     m = _lib.Model()
+    m.out_ld = out_ld
     m.graph = graph.c_struct()
     m.d, m.nclass, m.layers, m.strands = d, nclass, layers, strands
     m.training = 1 if training else 0
@@ -165,19 +172,21 @@ class _ChromeGCNFn(torch.autograd.Function):
             if ws_bytes == 0:
                 raise _lib.ChromeGCNNativeError("cgcn_model_workspace_bytes rejected n=%d d=%d" % (n, d))
             ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
-            out = torch.empty(n, nclass, dtype=torch.float32, device=dev)
+            ld = padded_classes(nclass)
+            out_buf = torch.empty(n, ld, dtype=torch.float32, device=dev)
+            out = out_buf
             gates = [torch.empty(n, 1, dtype=torch.float32, device=dev) for _ in range(layers)]
             seed, step = module._next_dropout_counter() if training else (0, 0)
             bn = module.batch_norm
             m = build_model_struct(graph, d, nclass, layers, 1, training, module.dropout, seed, step, params, None,
                                    bn.running_mean, bn.running_var, bn.num_batches_tracked, x, None, out, gates, None, ws,
-                                   module.gemm_impl, bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                                   module.gemm_impl, bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld)
             _lib.check(lib.cgcn_model_forward(C.byref(m)), "cgcn_model_forward")
         ctx.module, ctx.graph, ctx.names = module, graph, names
         ctx.cfg = (n, d, nclass, layers, training, seed, step)
-        ctx.save_for_backward(x, ws, out, *gates, *[params[k] for k in names])
+        ctx.save_for_backward(x, ws, out_buf, *gates, *[params[k] for k in names])
         ctx.mark_non_differentiable(*gates)
-        return (out, *gates)
+        return (out_buf[:, :nclass], *gates)
 
     @staticmethod
     def backward(ctx, dout, *unused):
@@ -189,14 +198,17 @@ class _ChromeGCNFn(torch.autograd.Function):
         gates = list(saved[3:3 + layers])
         params = dict(zip(names, saved[3 + layers:]))
         dev = x.device
-        dout = ops._f32c(dout)
+        ld = out.shape[1]
+        dpad = torch.zeros(n, ld, dtype=torch.float32, device=dev)
+        dpad[:, :nclass] = dout
+        dout = dpad
         with torch.cuda.device(dev):
             grads = {k: torch.empty_like(v) for k, v in params.items()}
             dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
             bn = module.batch_norm
             m = build_model_struct(graph, d, nclass, layers, 1, training, module.dropout, seed, step, params, grads,
                                    bn.running_mean, bn.running_var, None, x, dx, out, gates, dout, ws, module.gemm_impl,
-                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld)
             _lib.check(lib.cgcn_model_backward(C.byref(m)), "cgcn_model_backward")
         return (dx, None, None, *[grads[k] for k in names])
 

@@ -195,7 +195,7 @@ int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transp
 }
 
 // -------------------------------------------------------------------------------- gram
-constexpr int GRAM_MIN_ROWS = 256;    // rows per CTA (lower bound); the upper bound 4*SMs CTAs caps the partial tiles
+constexpr int GRAM_MIN_ROWS = 256;    // rows per CTA (lower bound); the upper bound 2*SMs CTAs caps the partial tiles
 
 struct GramArgs {
   const float* A;
@@ -295,23 +295,46 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_gram_kernel(const GramArgs p
   }
 }
 
-__global__ void gram_finalize_kernel(const float* __restrict__ partial, int parts, int count, float* __restrict__ C,
-                                     int nb, int64_t ldc, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= count) return;
-  double s = 0.0;
-  for (int q = 0; q < parts; ++q) s += static_cast<double>(partial[static_cast<size_t>(q) * count + idx]);
-  float* dst = C + static_cast<int64_t>(idx / nb) * ldc + (idx % nb);
-  *dst = accumulate ? static_cast<float>(static_cast<double>(*dst) + s) : static_cast<float>(s);
+// C (+)= sum over parts, fixed order: CTA = 64 output elements x 8 slices of the parts axis.
+// Part q holds its tile at partial + q*part_stride, element (i, j) at i*pld + j.
+__global__ void __launch_bounds__(512) gram_finalize_kernel(const float* __restrict__ partial, int parts, int part_stride,
+                                                            int pld, int ka, int nb, float* __restrict__ C, int64_t ldc,
+                                                            int accumulate) {
+  __shared__ double sh[8][64];
+  const int idx = blockIdx.x * 64 + threadIdx.x;
+  const int count = ka * nb;
+  const int i = idx / nb, j = idx - i * nb;
+  const size_t off = static_cast<size_t>(i) * pld + j;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (idx < count) {
+    int q = threadIdx.y;
+    for (; q + 24 < parts; q += 32) {
+      a0 += static_cast<double>(partial[static_cast<size_t>(q) * part_stride + off]);
+      a1 += static_cast<double>(partial[static_cast<size_t>(q + 8) * part_stride + off]);
+      a2 += static_cast<double>(partial[static_cast<size_t>(q + 16) * part_stride + off]);
+      a3 += static_cast<double>(partial[static_cast<size_t>(q + 24) * part_stride + off]);
+    }
+    for (; q < parts; q += 8) a0 += static_cast<double>(partial[static_cast<size_t>(q) * part_stride + off]);
+  }
+  sh[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < count) {
+    double s = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += sh[y][threadIdx.x];
+    float* dst = C + static_cast<int64_t>(i) * ldc + j;
+    *dst = accumulate ? static_cast<float>(static_cast<double>(*dst) + s) : static_cast<float>(s);
+  }
 }
 
-void gram_finalize_launch(const float* partial, int parts, int count, float* C, int nb, int64_t ldc, int accumulate,
-                          cudaStream_t stream) {
-  gram_finalize_kernel<<<(count + 255) / 256, 256, 0, stream>>>(partial, parts, count, C, nb, ldc, accumulate);
+void gram_finalize_launch(const float* partial, int parts, int part_stride, int pld, int ka, int nb, float* C,
+                          int64_t ldc, int accumulate, cudaStream_t stream) {
+  gram_finalize_kernel<<<(ka * nb + 63) / 64, dim3(64, 8), 0, stream>>>(partial, parts, part_stride, pld, ka, nb, C, ldc,
+                                                                        accumulate);
 }
 
 int64_t gram_rows_per_cta(int64_t m) {
-  const int64_t target = (m + 4LL * sm_count() - 1) / (4LL * sm_count());
+  const int64_t target = (m + 2LL * sm_count() - 1) / (2LL * sm_count());
   int64_t rows = target > GRAM_MIN_ROWS ? target : GRAM_MIN_ROWS;
   return (rows + GBK - 1) / GBK * GBK;
 }
@@ -339,8 +362,7 @@ int gemm_gram_ffma(const float* A, int64_t lda, const float* B, int64_t ldb, flo
   const int parts = static_cast<int>((m + p.rows_per_cta - 1) / p.rows_per_cta);
   gemm_gram_kernel<<<parts, GTHREADS, 0, stream>>>(p);
   CGCN_TRY(check_launch("gemm_gram_kernel"));
-  const int count = ka * nb;
-  gram_finalize_kernel<<<(count + 255) / 256, 256, 0, stream>>>(p.partial, parts, count, C, nb, ldc, accumulate);
+  gram_finalize_launch(p.partial, parts, ka * nb, nb, ka, nb, C, ldc, accumulate, stream);
   return check_launch("gram_finalize_kernel");
 }
 

@@ -6,8 +6,8 @@
 //   gram       C[128x128] = sum_r A[r,:]^T (x) B[r,:]                 weight gradients X^T G
 //
 // fp32 parity (<= 1e-5) rules out a single TF32 pass (8.8e-5).  Every fp32 operand v is
-// split in registers into hi = v & 0xffffe000 (exactly a TF32 number) and lo = v - hi (exact in fp32,
-// then truncated to TF32), and each tile accumulates hi*hi + lo*hi + hi*lo in the fp32 TMEM
+// split in registers into hi = rna_tf32(v) and lo = rna_tf32(v - hi) (the subtraction is exact in
+// fp32), and each tile accumulates hi*hi + lo*hi + hi*lo in the fp32 TMEM
 // accumulator: three kind::tf32 MMAs per k-step.  Because the split needs the operands in registers
 // anyway, tiles are staged global -> registers -> shared memory by producer warps that write the
 // UMMA canonical SWIZZLE_128B layout directly (no TMA descriptor): 16-byte chunk c of 128-byte row r
@@ -24,8 +24,8 @@
 
 namespace cgcn {
 
-void gram_finalize_launch(const float* partial, int parts, int count, float* C, int nb, int64_t ldc, int accumulate,
-                          cudaStream_t stream);
+void gram_finalize_launch(const float* partial, int parts, int part_stride, int pld, int ka, int nb, float* C,
+                          int64_t ldc, int accumulate, cudaStream_t stream);
 int64_t gram_rows_per_cta(int64_t m);
 size_t gram_workspace_bytes(int64_t m);
 
@@ -119,9 +119,13 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_maj
          ((128u >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// hi = round-to-nearest TF32 of v, lo = round-to-nearest TF32 of (v - hi).  Rounding (not
+// truncation) keeps the dropped remainder zero-mean, which matters for the weight-gradient sums:
+// they cancel heavily, and a one-signed truncation bias adds up coherently over 10^4..10^6 rows.
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(v) & 0xFFFFE000u;
-  lo = __float_as_uint(v - __uint_as_float(hi)) & 0xFFFFE000u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  const float rem = v - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rem));
 }
 __device__ __forceinline__ void split4(const float4 v, uint4& hi, uint4& lo) {
   split_tf32(v.x, hi.x, lo.x);
@@ -136,11 +140,13 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4 v) {
 // ------------------------------------------------------------------ B image (weights) preparation
 // img[(hi|lo)][kchunk 4][n 128][32 floats] in the K-major SWIZZLE_128B layout; Bw(n,k) is the weight
 // that multiplies A[:,k] into C[:,n].
-__global__ void tc_prep_b_kernel(const float* __restrict__ B, int b_transposed, uint32_t* __restrict__ img) {
+__global__ void tc_prep_b_kernel(const float* __restrict__ B, int b_transposed, int n_valid, int k_valid,
+                                 uint32_t* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= TILE * TILE) return;
   const int n = idx >> 7, k = idx & 127;
-  const float v = b_transposed ? __ldg(B + n * TILE + k) : __ldg(B + k * TILE + n);
+  float v = 0.f;                                               // zero padding up to 128 x 128
+  if (n < n_valid && k < k_valid) v = b_transposed ? __ldg(B + n * k_valid + k) : __ldg(B + k * n_valid + n);
   uint32_t hi, lo;
   split_tf32(v, hi, lo);
   const int kc = k >> 5, kk = k & 31;
@@ -160,6 +166,7 @@ struct RowPanelTcArgs {
   int64_t m;
   const int32_t* rowscale_rowptr;
   int rowscale_group;
+  int n_valid, k_valid;        // <= 128; A rows hold round_up(k_valid, 4) readable floats, C rows round_up(n_valid, 4) writable
 };
 
 constexpr int RP_B_BYTES = 2 * 4 * CHUNK_BYTES;                 // hi + lo, 4 k-chunks: 128 KB
@@ -228,7 +235,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
         const int u = pt + PROD_THREADS * i;
         const int r = u >> 3, c = u & 7;
         const int64_t grow = row0 + r;
-        v[kc][i] = (tile < tiles && grow < p.m) ? ldg4(p.A + grow * p.lda + kc * KCH + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int col = kc * KCH + c * 4;
+        v[kc][i] = (tile < tiles && grow < p.m && col < p.k_valid) ? ldg4(p.A + grow * p.lda + col) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
 #pragma unroll
@@ -310,14 +318,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
           float* dst = p.C + grow * p.ldc + cc * 32;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const int col = cc * 32 + 4 * j;
+            if (col >= p.n_valid) break;                        // columns beyond round_up(n_valid, 4) are never written
             float4 o = make_float4(__uint_as_float(r[4 * j]) * scale, __uint_as_float(r[4 * j + 1]) * scale,
                                    __uint_as_float(r[4 * j + 2]) * scale, __uint_as_float(r[4 * j + 3]) * scale);
             if (p.bias != nullptr) {
-              const float4 b = ldg4(p.bias + cc * 32 + 4 * j);
-              o.x += b.x;
-              o.y += b.y;
-              o.z += b.z;
-              o.w += b.w;
+              if (col + 3 < p.n_valid) {
+                const float4 b = ldg4(p.bias + col);
+                o.x += b.x;
+                o.y += b.y;
+                o.z += b.z;
+                o.w += b.w;
+              } else {
+                o.x += __ldg(p.bias + col);
+                if (col + 1 < p.n_valid) o.y += __ldg(p.bias + col + 1);
+                if (col + 2 < p.n_valid) o.z += __ldg(p.bias + col + 2);
+              }
             }
             st4(dst + 4 * j, o);
           }
@@ -345,6 +361,7 @@ struct GramTcArgs {
   int64_t m;
   int64_t rows_per_cta;        // multiple of 32
   float* partial;              // [gridDim.x][128][128]
+  int ka_valid, nb_valid;      // <= 128; rows hold round_up(valid, 4) readable floats
 };
 
 constexpr int GR_OP_BYTES = 2 * CHUNK_BYTES;                     // one operand, hi + lo, 32 rows x 128 cols: 32 KB
@@ -397,8 +414,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcAr
         const int r = u >> 5, c = u & 31;
         const int64_t grow = row0 + r;
         const bool ok = ch < chunks && grow < r_end;
-        va[slot][i] = ok ? ldg4(p.A + grow * p.lda + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[slot][i] = ok ? ldg4(p.B + grow * p.ldb + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        va[slot][i] = (ok && c * 4 < p.ka_valid) ? ldg4(p.A + grow * p.lda + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[slot][i] = (ok && c * 4 < p.nb_valid) ? ldg4(p.B + grow * p.ldb + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     issue(0, 0);
@@ -488,11 +505,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcAr
 // ------------------------------------------------------------------ host side
 static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
+static int up4(int v) { return (v + 3) / 4 * 4; }
 bool tc_rowpanel_supported(int64_t lda, int64_t ldc, int n, int k, const void* A, const void* C) {
-  return n == 128 && k == 128 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(C);
+  return n >= 1 && n <= 128 && k >= 1 && k <= 128 && lda % 4 == 0 && ldc % 4 == 0 && lda >= up4(k) && ldc >= up4(n) &&
+         aligned16(A) && aligned16(C);
 }
 bool tc_gram_supported(int64_t lda, int64_t ldb, int ka, int nb, const void* A, const void* B) {
-  return ka == 128 && nb == 128 && lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B);
+  return ka >= 1 && ka <= 128 && nb >= 1 && nb <= 128 && lda % 4 == 0 && ldb % 4 == 0 && lda >= up4(ka) && ldb >= up4(nb) &&
+         aligned16(A) && aligned16(B);
 }
 size_t tc_workspace_bytes() { return tc::RP_B_BYTES + 256; }
 
@@ -500,7 +520,8 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
                      int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   CGCN_REQUIRE(A && B && C, "cgcn_gemm_rowpanel: null operand");
-  CGCN_REQUIRE(tc_rowpanel_supported(lda, ldc, n, k, A, C), "cgcn_gemm_rowpanel(tcgen05): needs n = k = 128 and 16-byte aligned rows");
+  CGCN_REQUIRE(tc_rowpanel_supported(lda, ldc, n, k, A, C),
+               "cgcn_gemm_rowpanel(tcgen05): needs n, k <= 128 and 16-byte aligned rows padded to a multiple of 4 floats");
   CGCN_REQUIRE(bias == nullptr || aligned16(bias), "cgcn_gemm_rowpanel(tcgen05): bias must be 16-byte aligned");
   if (workspace == nullptr || workspace_bytes < tc_workspace_bytes() || !aligned16(workspace)) {
     set_error("cgcn_gemm_rowpanel(tcgen05): needs a %zu-byte, 16-byte aligned workspace", tc_workspace_bytes());
@@ -513,9 +534,9 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
     attr_set = true;
   }
   uint32_t* img = static_cast<uint32_t*>(workspace);
-  tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, img);
+  tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, n, k, img);
   CGCN_TRY(check_launch("tc_prep_b_kernel"));
-  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rowscale_rowptr, rowscale_group};
+  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rowscale_rowptr, rowscale_group, n, k};
   const int64_t tiles = (m + tc::TILE - 1) / tc::TILE;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   tc::gemm_rowpanel_tc_kernel<<<grid, tc::THREADS, tc::RP_SMEM, stream>>>(p);
@@ -525,7 +546,8 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
 int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
                  int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   CGCN_REQUIRE(A && B && C && m >= 1, "cgcn_gemm_gram: bad operand");
-  CGCN_REQUIRE(tc_gram_supported(lda, ldb, ka, nb, A, B), "cgcn_gemm_gram(tcgen05): needs ka = nb = 128 and 16-byte aligned rows");
+  CGCN_REQUIRE(tc_gram_supported(lda, ldb, ka, nb, A, B),
+               "cgcn_gemm_gram(tcgen05): needs ka, nb <= 128 and 16-byte aligned rows padded to a multiple of 4 floats");
   if (workspace == nullptr || workspace_bytes < gram_workspace_bytes(m) || !aligned16(workspace)) {
     set_error("cgcn_gemm_gram(tcgen05): workspace %zu < %zu bytes", workspace_bytes, gram_workspace_bytes(m));
     return CGCN_ERR_WORKSPACE;
@@ -538,10 +560,10 @@ int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float
   int64_t rows = gram_rows_per_cta(m);
   rows = (rows + tc::KCH - 1) / tc::KCH * tc::KCH;
   const int parts = static_cast<int>((m + rows - 1) / rows);
-  tc::GramTcArgs p{A, lda, B, ldb, m, rows, static_cast<float*>(workspace)};
+  tc::GramTcArgs p{A, lda, B, ldb, m, rows, static_cast<float*>(workspace), ka, nb};
   tc::gemm_gram_tc_kernel<<<parts, tc::THREADS, tc::GR_SMEM, stream>>>(p);
   CGCN_TRY(check_launch("gemm_gram_tc_kernel"));
-  gram_finalize_launch(p.partial, parts, 128 * 128, C, 128, ldc, accumulate, stream);
+  gram_finalize_launch(p.partial, parts, tc::TILE * tc::TILE, tc::TILE, ka, nb, C, ldc, accumulate, stream);
   return check_launch("gram_finalize_kernel");
 }
 

@@ -34,9 +34,9 @@ size_t tc_workspace_bytes();
 
 int rowwise_max_grid();
 int bce_grid();
-int bce_launch(const float* out, const float* target, int n, int C, int S, float* probs, float* loss_sum,
+int bce_launch(const float* out, const float* target, int n, int C, int S, int ld, float* probs, float* loss_sum,
                float* out_grad, float* partial, cudaStream_t stream);
-int colsum_launch(const float* X, int64_t rows, int cols, float* dst, float* partial, cudaStream_t stream);
+int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* dst, float* partial, cudaStream_t stream);
 int bn_finalize_launch(const float* partial, int parts, int n, int S, int D, float eps, float momentum, int training,
                        float* running_mean, float* running_var, int64_t* nbt, float* mean_out, float* rstd_out,
                        cudaStream_t stream);
@@ -72,7 +72,7 @@ int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_tr
                            int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
   const bool tc_ok = tc_rowpanel_supported(lda, ldc, n, k, A, C) && ws != nullptr && ws_bytes >= tc_workspace_bytes();
   if (impl == 2 && !tc_ok) {
-    set_error("cgcn_gemm_rowpanel: tcgen05 path needs n = k = 128, 16-byte aligned rows and a workspace");
+    set_error("cgcn_gemm_rowpanel: tcgen05 path needs n, k <= 128, 16-byte aligned rows of a multiple of 4 floats and a workspace");
     return CGCN_ERR_INVALID;
   }
   if (impl == 2 || (impl == 0 && tc_ok))
@@ -85,7 +85,7 @@ int gemm_gram_dispatch(const float* A, int64_t lda, const float* B, int64_t ldb,
                        int ka, int nb, int accumulate, int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
   const bool tc_ok = tc_gram_supported(lda, ldb, ka, nb, A, B);
   if (impl == 2 && !tc_ok) {
-    set_error("cgcn_gemm_gram: tcgen05 path needs ka = nb = 128 and 16-byte aligned rows");
+    set_error("cgcn_gemm_gram: tcgen05 path needs ka, nb <= 128 and 16-byte aligned rows of a multiple of 4 floats");
     return CGCN_ERR_INVALID;
   }
   if (impl == 2 || (impl == 0 && tc_ok))
@@ -150,6 +150,7 @@ static int validate(const cgcn_model* m, bool backward) {
   CGCN_REQUIRE(m->layers == 1 || m->layers == 2, "cgcn_model: layers=%d", m->layers);
   CGCN_REQUIRE(m->strands == 1 || m->strands == 2, "cgcn_model: strands=%d", m->strands);
   CGCN_REQUIRE(m->dropout_p >= 0.f && m->dropout_p < 1.f, "cgcn_model: dropout_p=%f", m->dropout_p);
+  CGCN_REQUIRE(m->out_ld == 0 || m->out_ld >= m->nclass, "cgcn_model: out_ld=%d < nclass=%d", m->out_ld, m->nclass);
   CGCN_REQUIRE(m->x_in && m->out && m->gate[0] && (m->layers == 1 || m->gate[1]), "cgcn_model: null activation pointer");
   CGCN_REQUIRE(m->bn_running_mean && m->bn_running_var, "cgcn_model: null BatchNorm running statistics");
   for (int l = 0; l < m->layers; ++l)
@@ -231,7 +232,8 @@ static int model_forward(const cgcn_model* m) {
   b.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training);
   CGCN_TRY(bn_apply_launch(b, st));
   // out = hb Wout^T + bout                           (models/ChromeModels.py:51)
-  CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.hb, d, m->params.out_w, 1, m->params.out_b, m->out, C, M, C, d, nullptr, 1,
+  const int ldo = m->out_ld > 0 ? m->out_ld : C;
+  CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.hb, d, m->params.out_w, 1, m->params.out_b, m->out, ldo, M, C, d, nullptr, 1,
                                   m->gemm_impl, tcws, lay.tc_bytes, st));
   return CGCN_OK;
 }
@@ -251,10 +253,11 @@ static int model_backward(const cgcn_model* m) {
   void* gram_ws = ws + lay.gram;
 
   // head: d out.weight = dout^T hb ; d out.bias = colsum(dout) ; d hb = dout Wout
-  CGCN_TRY(gemm_gram_dispatch(m->out_grad, C, ws + lay.hb, d, m->grads.out_w, d, M, C, d, 0, m->gemm_impl, gram_ws,
+  const int ldo = m->out_ld > 0 ? m->out_ld : C;
+  CGCN_TRY(gemm_gram_dispatch(m->out_grad, ldo, ws + lay.hb, d, m->grads.out_w, d, M, C, d, 0, m->gemm_impl, gram_ws,
                               lay.gram_bytes, st));
-  CGCN_TRY(colsum_launch(m->out_grad, M, C, m->grads.out_b, ws + lay.partial, st));
-  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, C, m->params.out_w, 0, nullptr, dA, d, M, d, C, nullptr, 1, m->gemm_impl,
+  CGCN_TRY(colsum_launch(m->out_grad, M, C, ldo, m->grads.out_b, ws + lay.partial, st));
+  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, ldo, m->params.out_w, 0, nullptr, dA, d, M, d, C, nullptr, 1, m->gemm_impl,
                                   tcws, lay.tc_bytes, st));
   // BatchNorm backward sums
   {
@@ -357,8 +360,8 @@ extern "C" int cgcn_train_step(const cgcn_model* m, const float* target, float* 
   CGCN_REQUIRE(m && target && loss_sum_out && out_grad_scratch, "cgcn_train_step: null argument");
   CGCN_TRY(model_forward(m));
   const WsLayout lay = make_layout(m->graph.n, m->d, m->nclass, m->layers, m->strands);
-  CGCN_TRY(bce_launch(m->out, target, m->graph.n, m->nclass, m->strands, probs, loss_sum_out, out_grad_scratch,
-                      m->workspace + lay.partial, static_cast<cudaStream_t>(m->stream)));
+  CGCN_TRY(bce_launch(m->out, target, m->graph.n, m->nclass, m->strands, m->out_ld > 0 ? m->out_ld : m->nclass, probs,
+                      loss_sum_out, out_grad_scratch, m->workspace + lay.partial, static_cast<cudaStream_t>(m->stream)));
   cgcn_model mb = *m;
   mb.out_grad = out_grad_scratch;
   return model_backward(&mb);

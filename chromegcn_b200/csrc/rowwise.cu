@@ -48,7 +48,7 @@ __device__ __forceinline__ void block_combine(float* red, int K, float* __restri
 
 // Fixed-order parallel reduction of per-CTA partials: a CTA of (32 columns) x (FIN_SLICES slices of the
 // parts axis); every thread sums its slice in fp64, slices are combined in slice order in shared memory.
-constexpr int FIN_SLICES = 16;
+constexpr int FIN_SLICES = 32;
 
 template <int NV>
 __device__ __forceinline__ void reduce_parts(const float* __restrict__ partial, int parts, size_t stride,
@@ -58,7 +58,19 @@ __device__ __forceinline__ void reduce_parts(const float* __restrict__ partial, 
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = 0.0;
   if (active) {
-    for (int q = threadIdx.y; q < parts; q += FIN_SLICES) {
+    int q = threadIdx.y;
+    for (; q + 3 * FIN_SLICES < parts; q += 4 * FIN_SLICES) {       // 4 x NV independent loads in flight
+      float t[4][NV];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) t[u][v] = partial[static_cast<size_t>(q + u * FIN_SLICES) * stride + offs[v]];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] += static_cast<double>(t[u][v]);
+    }
+    for (; q < parts; q += FIN_SLICES) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) acc[v] += static_cast<double>(partial[static_cast<size_t>(q) * stride + offs[v]]);
     }
@@ -385,7 +397,7 @@ __global__ void __launch_bounds__(32 * FIN_SLICES) col_finalize_kernel(const Col
 // ------------------------------------------------------------------------------ generic column sum
 // dst[c] = sum_r X[r][c], X [rows][cols] with arbitrary cols <= 128 (d out.bias = column sums of the
 // logit gradient).  One thread per column, 8 rows in flight.
-__global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols,
+__global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols, int ld,
                                                              int64_t rows_per_cta, float* __restrict__ partial) {
   const int c = threadIdx.x;
   const int64_t r0 = blockIdx.x * rows_per_cta;
@@ -395,9 +407,9 @@ __global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __rest
     int64_t r = r0;
     for (; r + 8 <= r1; r += 8) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += __ldg(X + (r + u) * cols + c);
+      for (int u = 0; u < 8; ++u) acc[u] += __ldg(X + (r + u) * ld + c);
     }
-    for (; r < r1; ++r) acc[0] += __ldg(X + r * cols + c);
+    for (; r < r1; ++r) acc[0] += __ldg(X + r * ld + c);
   }
   const float t = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   partial[static_cast<size_t>(blockIdx.x) * 128 + c] = (c < cols) ? t : 0.f;
@@ -410,8 +422,8 @@ struct BceArgs {
   float* probs;        // [n][C] or NULL
   float* out_grad;     // [n][S][C] or NULL
   float* partial;      // [grid]
-  int64_t total;       // n*C
-  int C, S;
+  int64_t total;       // n*ld
+  int C, S, ld;        // ld = floats per (row, strand) of out / out_grad
   float inv_count;     // 1 / (n*C)
 };
 
@@ -419,20 +431,46 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
   __shared__ float wsum[8];
   float local = 0.f;
   const float inv_s = 1.0f / a.S;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < a.total;
-       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = e / a.C;
-    const int c = static_cast<int>(e - r * a.C);
-    float p = 0.f;
-    for (int s = 0; s < a.S; ++s) p += __ldg(a.out + (r * a.S + s) * a.C + c);
-    p *= inv_s;                                               // (pred_f + pred_r) / 2, finetune.py:43
-    const float t = __ldg(a.target + e);
-    local += fmaxf(p, 0.f) - p * t + log1pf(expf(-fabsf(p)));  // F.binary_cross_entropy_with_logits, finetune.py:45
-    const float pr = sigmoidf_(p);
-    if (a.probs != nullptr) a.probs[e] = pr;                  // F.sigmoid(pred), finetune.py:52
-    if (a.out_grad != nullptr) {
-      const float gsc = (pr - t) * a.inv_count * inv_s;
-      for (int s = 0; s < a.S; ++s) a.out_grad[(r * a.S + s) * a.C + c] = gsc;
+  const uint32_t total = static_cast<uint32_t>(a.total), C = static_cast<uint32_t>(a.C), S = static_cast<uint32_t>(a.S);
+  const uint32_t LD = static_cast<uint32_t>(a.ld);
+  // flat over the n x ld elements (padding columns only get a zero gradient), 4 independent elements per
+  // thread per trip (coalesced, 32-bit index math)
+  for (uint32_t e0 = blockIdx.x * 1024u + threadIdx.x; e0 < total; e0 += gridDim.x * 1024u) {
+    float p[4], t[4];
+    uint32_t ob[4], rr[4], cc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t e = e0 + u * 256u;
+      p[u] = 0.f;
+      t[u] = 0.f;
+      ob[u] = rr[u] = cc[u] = 0;
+      if (e < total) {
+        rr[u] = e / LD;
+        cc[u] = e - rr[u] * LD;
+        ob[u] = rr[u] * S * LD + cc[u];                         // (r*S + 0)*ld + c
+        if (cc[u] < C) {
+          for (uint32_t s = 0; s < S; ++s) p[u] += __ldg(a.out + ob[u] + s * LD);
+          t[u] = __ldg(a.target + rr[u] * C + cc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t e = e0 + u * 256u;
+      if (e >= total) continue;
+      if (cc[u] >= C) {
+        if (a.out_grad != nullptr)
+          for (uint32_t s = 0; s < S; ++s) a.out_grad[ob[u] + s * LD] = 0.f;
+        continue;
+      }
+      const float pm = p[u] * inv_s;                            // (pred_f + pred_r) / 2, finetune.py:43
+      local += fmaxf(pm, 0.f) - pm * t[u] + log1pf(expf(-fabsf(pm)));   // BCE-with-logits, finetune.py:45
+      const float pr = sigmoidf_(pm);
+      if (a.probs != nullptr) a.probs[rr[u] * C + cc[u]] = pr;  // F.sigmoid(pred), finetune.py:52
+      if (a.out_grad != nullptr) {
+        const float gsc = (pr - t[u]) * a.inv_count * inv_s;
+        for (uint32_t s = 0; s < S; ++s) a.out_grad[ob[u] + s * LD] = gsc;
+      }
     }
   }
   local = warp_sum(local);
@@ -633,13 +671,13 @@ size_t colsum_workspace_floats(int64_t rows) {
   return static_cast<size_t>(sm_count()) * 8 * 128;
 }
 
-int colsum_launch(const float* X, int64_t rows, int cols, float* dst, float* partial, cudaStream_t stream) {
+int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* dst, float* partial, cudaStream_t stream) {
   CGCN_REQUIRE(cols >= 1 && cols <= 128, "colsum: cols=%d", cols);
   const int64_t max_parts = static_cast<int64_t>(sm_count()) * 8;
   int64_t rows_per = (rows + max_parts - 1) / max_parts;
   if (rows_per < 64) rows_per = 64;
   const int parts = static_cast<int>((rows + rows_per - 1) / rows_per);
-  colsum_partial_kernel<<<parts, 128, 0, stream>>>(X, rows, cols, rows_per, partial);
+  colsum_partial_kernel<<<parts, 128, 0, stream>>>(X, rows, cols, ld, rows_per, partial);
   CGCN_TRY(check_launch("colsum_partial_kernel"));
   ColFinalizeArgs f{};
   f.partial = partial;
@@ -652,11 +690,12 @@ int colsum_launch(const float* X, int64_t rows, int cols, float* dst, float* par
 
 int bce_grid() { return sm_count() * 8; }
 
-int bce_launch(const float* out, const float* target, int n, int C, int S, float* probs, float* loss_sum,
+int bce_launch(const float* out, const float* target, int n, int C, int S, int ld, float* probs, float* loss_sum,
                float* out_grad, float* partial, cudaStream_t stream) {
-  BceArgs a{out, target, probs, out_grad, partial, static_cast<int64_t>(n) * C, C, S,
+  BceArgs a{out, target, probs, out_grad, partial, static_cast<int64_t>(n) * ld, C, S, ld,
             static_cast<float>(1.0 / (static_cast<double>(n) * C))};
-  int grid = static_cast<int>((a.total + 255) / 256);
+  CGCN_REQUIRE(a.total * S < 4294967296LL, "cgcn_bce_loss: n * nclass * strands must fit 32 bits");
+  int grid = static_cast<int>((a.total + 1023) / 1024);
   if (grid > bce_grid()) grid = bce_grid();
   if (grid < 1) grid = 1;
   bce_kernel<<<grid, 256, 0, stream>>>(a);
@@ -676,16 +715,18 @@ extern "C" size_t cgcn_bce_workspace_bytes(int32_t n, int32_t nclass) {
 }
 
 extern "C" int cgcn_bce_loss(const float* out, const float* target, int32_t n, int32_t nclass, int32_t strands,
-                             float* probs, float* loss_sum_out, float* out_grad, void* workspace,
+                             int32_t out_ld, float* probs, float* loss_sum_out, float* out_grad, void* workspace,
                              size_t workspace_bytes, cgcn_stream_t stream) {
   CGCN_REQUIRE(out && target && loss_sum_out, "cgcn_bce_loss: null argument");
   CGCN_REQUIRE(n >= 1 && nclass >= 1 && (strands == 1 || strands == 2), "cgcn_bce_loss: bad shape");
+  if (out_ld <= 0) out_ld = nclass;
+  CGCN_REQUIRE(out_ld >= nclass, "cgcn_bce_loss: out_ld %d < nclass %d", out_ld, nclass);
   if (workspace == nullptr || workspace_bytes < cgcn_bce_workspace_bytes(n, nclass)) {
     set_error("cgcn_bce_loss: workspace too small");
     return CGCN_ERR_WORKSPACE;
   }
-  return bce_launch(out, target, n, nclass, strands, probs, loss_sum_out, out_grad, static_cast<float*>(workspace),
-                    static_cast<cudaStream_t>(stream));
+  return bce_launch(out, target, n, nclass, strands, out_ld, probs, loss_sum_out, out_grad,
+                    static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cgcn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t count, float lr,

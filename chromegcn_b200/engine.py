@@ -18,7 +18,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib, ops
-from .chrome_models import ChromeGCN, build_model_struct
+from .chrome_models import ChromeGCN, build_model_struct, padded_classes
 from .graph import HiCGraph
 
 _SLOT = 64  # floats: every parameter starts on a 256-byte boundary inside the flat buffer
@@ -114,7 +114,7 @@ class ChromosomeEngine:
     def run(self, graph: HiCGraph, panel: torch.Tensor, target: torch.Tensor, probs_out: Optional[torch.Tensor],
             loss_slot: torch.Tensor, train: bool, input_grad: Optional[torch.Tensor] = None):
         """One chromosome: forward (+ loss, + backward when `train`).  Gradients land in the model's flat
-        gradient buffer (== every parameter's .grad).  Returns `(out [n, S, C], gates)` views that stay
+        gradient buffer (== every parameter's .grad).  Returns `(out [n, S, C] (a strided view), gates)` that stay
         valid until the next call."""
         lib = _lib.load()
         model = self.model
@@ -128,9 +128,10 @@ class ChromosomeEngine:
             if ws_bytes == 0:
                 raise _lib.ChromeGCNNativeError("cgcn_model_workspace_bytes rejected n=%d d=%d" % (n, d))
             ws = self._buf("ws", ws_bytes // 4)
-            out = self._buf("out", n * S * nclass)[: n * S * nclass].view(n, S, nclass)
+            ld = padded_classes(nclass)
+            out = self._buf("out", n * S * ld)[: n * S * ld].view(n, S, ld)
             gates = [self._buf("gate%d" % l, n * S)[: n * S].view(n, S) for l in range(layers)]
-            dout = self._buf("dout", n * S * nclass)[: n * S * nclass].view(n, S, nclass)
+            dout = self._buf("dout", n * S * ld)[: n * S * ld].view(n, S, ld)
             seed, step = model._next_dropout_counter() if model.training else (0, 0)
             bn = model.batch_norm
             params = fp.views(fp.flat)
@@ -138,7 +139,7 @@ class ChromosomeEngine:
             m = build_model_struct(graph, d, nclass, layers, S, model.training, model.dropout, seed, step, params,
                                    grads if train else None, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                                    panel, input_grad, out, gates, None, ws, model.gemm_impl,
-                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld)
             tgt = ops._f32c(target)
             if train:
                 _lib.check(lib.cgcn_train_step(C.byref(m), tgt.data_ptr(), _lib.ptr(probs_out), loss_slot.data_ptr(),
@@ -147,8 +148,8 @@ class ChromosomeEngine:
             else:
                 _lib.check(lib.cgcn_model_forward(C.byref(m)), "cgcn_model_forward")
                 bce_ws = self._buf("bce_ws", lib.cgcn_bce_workspace_bytes(n, nclass) // 4 + 64)
-                _lib.check(lib.cgcn_bce_loss(out.data_ptr(), tgt.data_ptr(), n, nclass, S, _lib.ptr(probs_out),
+                _lib.check(lib.cgcn_bce_loss(out.data_ptr(), tgt.data_ptr(), n, nclass, S, ld, _lib.ptr(probs_out),
                                              loss_slot.data_ptr(), None, bce_ws.data_ptr(), bce_ws.numel() * 4,
                                              _lib.current_stream()), "cgcn_bce_loss")
         self.step_count += 1
-        return out, gates
+        return out[:, :, :nclass], gates

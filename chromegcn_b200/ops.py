@@ -92,12 +92,13 @@ def bce_loss(out: torch.Tensor, target: torch.Tensor, strands: int, loss_acc: to
     lib = _lib.load()
     out, target = _f32c(out), _f32c(target)
     n, c = target.shape
+    ld = out.shape[-1]                       # row pitch of the logits (>= nclass)
     probs = torch.empty(n, c, dtype=torch.float32, device=out.device) if want_probs else None
     grad = torch.empty_like(out) if want_grad else None
     with torch.cuda.device(out.device):
         need = lib.cgcn_bce_workspace_bytes(n, c)
         ws = torch.empty(need, dtype=torch.uint8, device=out.device)
-        _lib.check(lib.cgcn_bce_loss(out.data_ptr(), target.data_ptr(), n, c, strands, _lib.ptr(probs),
+        _lib.check(lib.cgcn_bce_loss(out.data_ptr(), target.data_ptr(), n, c, strands, ld, _lib.ptr(probs),
                                      loss_acc.data_ptr(), _lib.ptr(grad), ws.data_ptr(), need, _lib.current_stream()),
                    "cgcn_bce_loss")
     return probs, grad

@@ -133,7 +133,7 @@ int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, in
  * b_transposed 1: B is [n][k] row-major (nn.Linear weight, models/ChromeModels.py:51).
  * bias [n] or NULL.  rowscale_rowptr: NULL, or the graph's rowptr: row r is scaled by
  * 1/deg(r / rowscale_group) (the D^-1 of A_hat^T applied to the input of the backward SpMM).
- * k, n <= 128.
+ * k, n <= 128.  The tcgen05 path needs lda, ldc multiples of 4 (rows padded to round_up(k|n, 4) floats).
  */
 int cgcn_gemm_rowpanel(const float* A, int64_t lda, const float* B, int32_t b_transposed, const float* bias,
                        float* C, int64_t ldc, int64_t m, int32_t n, int32_t k,
@@ -175,7 +175,9 @@ typedef struct cgcn_model {
   int32_t training;       /* BatchNorm batch statistics + dropout (ChromeModel.train()) */
   int32_t gemm_impl;      /* see above */
   int32_t need_input_grad;/* also produce d loss / d x_in (finetune.py:33-34 asks, nothing reads it) */
-  int32_t reserved0;
+  int32_t out_ld;         /* floats per (row, strand) of `out` and `out_grad`, >= nclass; 0 = nclass.  A multiple of 4
+                             (e.g. 104 for nclass 103) puts the head contractions on the tcgen05 path; padding columns of
+                             `out` are zero-filled and those of `out_grad` must be finite */
   float dropout_p;        /* F.dropout p (models/ChromeModels.py:42,50) */
   float bn_momentum;      /* 0.1 */
   float bn_eps;           /* 1e-5 */
@@ -189,9 +191,9 @@ typedef struct cgcn_model {
   int64_t* bn_num_batches_tracked; /* [1] */
   const float* x_in;      /* [n][strands][d] */
   float* x_in_grad;       /* [n][strands][d] or NULL */
-  float* out;             /* [n][strands][nclass] logits (models/ChromeModels.py:51) */
+  float* out;             /* [n][strands][out_ld] logits in the first nclass columns (models/ChromeModels.py:51) */
   float* gate[2];         /* [n][strands] g, g2 (models/ChromeModels.py:39,45) */
-  const float* out_grad;  /* [n][strands][nclass], input of backward */
+  const float* out_grad;  /* [n][strands][out_ld], input of backward */
   float* workspace;       /* cgcn_model_workspace_bytes() bytes, kept from forward to backward */
   size_t workspace_bytes;
   cgcn_stream_t stream;
@@ -205,12 +207,12 @@ int cgcn_model_backward(const cgcn_model* m);
 
 /*
  * finetune.py:43-45,52: pred = mean over strands of the logits; loss = BCE-with-logits, mean over
- * n x nclass; probs = sigmoid(pred).  Writes loss_sum_out[0] += loss (a device accumulator, like
- * `total_loss += loss.item()` without the sync), probs [n][nclass] (may be NULL), and, if
- * out_grad != NULL, d loss / d out [n][strands][nclass].
+ * n x nclass; probs = sigmoid(pred).  `out` and `out_grad` rows are out_ld floats apart (>= nclass).
+ * Writes loss_sum_out[0] += loss (a device accumulator, like `total_loss += loss.item()` without the
+ * sync), probs [n][nclass] (may be NULL), and, if out_grad != NULL, d loss / d out (padding columns 0).
  */
 size_t cgcn_bce_workspace_bytes(int32_t n, int32_t nclass);
-int cgcn_bce_loss(const float* out, const float* target, int32_t n, int32_t nclass, int32_t strands,
+int cgcn_bce_loss(const float* out, const float* target, int32_t n, int32_t nclass, int32_t strands, int32_t out_ld,
                   float* probs, float* loss_sum_out, float* out_grad,
                   void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
 
