@@ -20,6 +20,8 @@
 //               fence.proxy.async, mbarrier arrive
 // Pipelines: smem stage full/empty mbarriers (producers <-> MMA, freed by tcgen05.commit) and, in
 // the row-panel kernel, a double-buffered TMEM accumulator (MMA <-> epilogue).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cgcn {
@@ -35,7 +37,10 @@ constexpr int TILE = 128;
 constexpr int KCH = 32;                               // floats per 128-byte swizzle row
 constexpr int ATOM_BYTES = 1024;                      // 8 rows x 128 B
 constexpr int CHUNK_BYTES = TILE * KCH * 4;           // 128 rows x 128 B = 16 KB
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;                             // gram kernel
+constexpr int RP_STAGES = 2;                          // row-panel kernel (B image + epilogue staging need the room)
+constexpr int STG_PITCH = 36;                         // floats per staged row: 128-bit accesses stay bank-conflict free
+constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;     // 4 epilogue warps x 32 rows x 36 floats = 18 KB
 constexpr int NUM_EPI_WARPS = 4, NUM_PROD_WARPS = 8;
 constexpr int MMA_WARP = NUM_EPI_WARPS;
 constexpr int THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;      // 416
@@ -136,6 +141,39 @@ __device__ __forceinline__ void split4(const float4 v, uint4& hi, uint4& lo) {
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+
+// Epilogue write-out of one 32-row x 32-column accumulator block held "thread = row" (tcgen05.ld 32x32b):
+// a row-per-thread global store would touch 32 different 128-byte lines per instruction (measured: 15 k
+// cycles per tile).  Stage through a padded per-warp shared-memory block instead and let 8 lanes write
+// one contiguous 128-byte row segment: 4 full lines per warp instruction.
+__device__ __forceinline__ void store_block_coalesced(uint32_t stg, const uint4 (&o)[8], int lane, float* __restrict__ dst_base,
+                                                      int64_t ld, int64_t row_first, int64_t row_limit, int col0,
+                                                      int col_limit) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sts128(stg + (lane * STG_PITCH + 4 * j) * 4, o[j]);
+  __syncwarp();
+  const int q = lane & 7, rsub = lane >> 3;
+  uint4 v[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) v[it] = lds128(stg + ((it * 4 + rsub) * STG_PITCH + 4 * q) * 4);
+  const int col = col0 + 4 * q;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int64_t grow = row_first + it * 4 + rsub;
+    if (grow < row_limit && col < col_limit) *reinterpret_cast<uint4*>(dst_base + grow * ld + col) = v[it];
+  }
+  __syncwarp();
+}
 
 // ------------------------------------------------------------------ B image (weights) preparation
 // img[(hi|lo)][kchunk 4][n 128][32 floats] in the K-major SWIZZLE_128B layout; Bw(n,k) is the weight
@@ -167,24 +205,35 @@ struct RowPanelTcArgs {
   const int32_t* rowscale_rowptr;
   int rowscale_group;
   int n_valid, k_valid;        // <= 128; A rows hold round_up(k_valid, 4) readable floats, C rows round_up(n_valid, 4) writable
+  long long* trace;            // developer aid (CGCN_TC_TRACE=1): per-role clock64() stamps of CTA 0, else NULL
 };
+
+#define TC_TRACE(slot, idx)                                                                   \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (idx) < 64) p.trace[(slot) * 64 + (idx)] = clock64(); \
+  } while (0)
 
 constexpr int RP_B_BYTES = 2 * 4 * CHUNK_BYTES;                 // hi + lo, 4 k-chunks: 128 KB
 constexpr int RP_STAGE_BYTES = 2 * CHUNK_BYTES;                 // A hi + lo of one k-chunk: 32 KB
-constexpr int RP_SMEM = RP_B_BYTES + STAGES * RP_STAGE_BYTES + 256 + 1024;
+constexpr int RP_SMEM = RP_B_BYTES + RP_STAGES * RP_STAGE_BYTES + STG_BYTES + 256 + 512 + 1024;   // + barriers + bias
 
 __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowPanelTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base;
   const uint32_t sA = base + RP_B_BYTES;
-  const uint32_t sBar = sA + STAGES * RP_STAGE_BYTES;           // full[3] empty[3] tfull[2] tempty[2] | tmem ptr
-  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tfull = sBar + 16 * STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t sStg = sA + RP_STAGES * RP_STAGE_BYTES;        // epilogue staging, 4 warps x 4.5 KB
+  const uint32_t sBar = sStg + STG_BYTES;                       // full[S] empty[S] tfull[2] tempty[2] | tmem ptr
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * RP_STAGES, bar_tfull = sBar + 16 * RP_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t s_tmem_ptr = bar_tempty + 16;
+  const uint32_t sBias = sBar + 256;                            // 128 floats (zero padded): the L1 is all shared memory here
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));        // generic pointer to the aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles = (p.m + TILE - 1) / TILE;
+  if (threadIdx.x < TILE)
+    reinterpret_cast<float*>(gen + (sBias - base))[threadIdx.x] =
+        (p.bias != nullptr && static_cast<int>(threadIdx.x) < p.n_valid) ? __ldg(p.bias + threadIdx.x) : 0.f;
 
   // B image: global -> smem (already swizzled), all threads
   {
@@ -205,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
     }
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < RP_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, NUM_PROD_WARPS);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -245,6 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (warp == MMA_WARP + 1) TC_TRACE(0, static_cast<int>((tile - blockIdx.x) / gridDim.x) * 4 + kc);
         const uint32_t sHi = sA + stage * RP_STAGE_BYTES, sLo = sHi + CHUNK_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -256,11 +306,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
           sts128(sHi + off, hi);
           sts128(sLo + off, lo);
         }
+        if (warp == MMA_WARP + 1) TC_TRACE(1, static_cast<int>((tile - blockIdx.x) / gridDim.x) * 4 + kc);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        if (warp == MMA_WARP + 1) TC_TRACE(2, static_cast<int>((tile - blockIdx.x) / gridDim.x) * 4 + kc);
         issue(tile + gridDim.x, kc);                            // refill this slot for the next tile
-        if (++stage == STAGES) {
+        if (++stage == RP_STAGES) {
           stage = 0;
           phase ^= 1;
         }
@@ -278,6 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
       for (int kc = 0; kc < 4; ++kc) {
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
+        TC_TRACE(3, static_cast<int>(it) * 4 + kc);
         if (lane == 0) {
           const uint32_t aHi = sA + stage * RP_STAGE_BYTES, aLo = aHi + CHUNK_BYTES;
           const uint32_t bHi = sB + kc * CHUNK_BYTES, bLo = bHi + 4 * CHUNK_BYTES;
@@ -292,8 +345,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
           umma_commit(bar_empty + 8 * stage);                     // frees the stage when these MMAs retire
           if (kc == 3) umma_commit(bar_tfull + 8 * acc);          // accumulator complete
         }
+        TC_TRACE(4, static_cast<int>(it) * 4 + kc);
         __syncwarp();
-        if (++stage == STAGES) {
+        if (++stage == RP_STAGES) {
           stage = 0;
           phase ^= 1;
         }
@@ -310,34 +364,29 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
       float scale = 1.0f;
       if (p.rowscale_rowptr != nullptr && grow < p.m)
         scale = inv_degree(p.rowscale_rowptr, static_cast<int>(grow / p.rowscale_group));
+      const uint32_t stg = sStg + warp * (32 * STG_PITCH * 4);
+      const int n_store = (p.n_valid + 3) & ~3;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
+        if (cc * 32 >= n_store) break;                          // warp-uniform
         uint32_t r[32];
+        if (warp == 0) TC_TRACE(5, static_cast<int>(it) * 8 + cc * 2);
         tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * TILE + cc * 32, r);
-        if (grow < p.m) {
-          float* dst = p.C + grow * p.ldc + cc * 32;
+        if (warp == 0) TC_TRACE(5, static_cast<int>(it) * 8 + cc * 2 + 1);
+        uint4 o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = cc * 32 + 4 * j;
-            if (col >= p.n_valid) break;                        // columns beyond round_up(n_valid, 4) are never written
-            float4 o = make_float4(__uint_as_float(r[4 * j]) * scale, __uint_as_float(r[4 * j + 1]) * scale,
-                                   __uint_as_float(r[4 * j + 2]) * scale, __uint_as_float(r[4 * j + 3]) * scale);
-            if (p.bias != nullptr) {
-              if (col + 3 < p.n_valid) {
-                const float4 b = ldg4(p.bias + col);
-                o.x += b.x;
-                o.y += b.y;
-                o.z += b.z;
-                o.w += b.w;
-              } else {
-                o.x += __ldg(p.bias + col);
-                if (col + 1 < p.n_valid) o.y += __ldg(p.bias + col + 1);
-                if (col + 2 < p.n_valid) o.z += __ldg(p.bias + col + 2);
-              }
-            }
-            st4(dst + 4 * j, o);
-          }
+        for (int j = 0; j < 8; ++j) {
+          const int col = cc * 32 + 4 * j;
+          const uint4 bq = lds128(sBias + col * 4);             // broadcast read, zero beyond n_valid
+          const float4 f = make_float4(fmaf(__uint_as_float(r[4 * j]), scale, __uint_as_float(bq.x)),
+                                       fmaf(__uint_as_float(r[4 * j + 1]), scale, __uint_as_float(bq.y)),
+                                       fmaf(__uint_as_float(r[4 * j + 2]), scale, __uint_as_float(bq.z)),
+                                       fmaf(__uint_as_float(r[4 * j + 3]), scale, __uint_as_float(bq.w)));
+          o[j] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
         }
+        if (warp == 0) TC_TRACE(6, static_cast<int>(it) * 8 + cc * 2);
+        store_block_coalesced(stg, o, lane, p.C, p.ldc, tile * TILE + warp * 32, p.m, cc * 32, n_store);
+        if (warp == 0) TC_TRACE(6, static_cast<int>(it) * 8 + cc * 2 + 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -366,13 +415,14 @@ struct GramTcArgs {
 
 constexpr int GR_OP_BYTES = 2 * CHUNK_BYTES;                     // one operand, hi + lo, 32 rows x 128 cols: 32 KB
 constexpr int GR_STAGE_BYTES = 2 * GR_OP_BYTES;                  // A + B: 64 KB
-constexpr int GR_SMEM = STAGES * GR_STAGE_BYTES + 256 + 1024;
+constexpr int GR_SMEM = STAGES * GR_STAGE_BYTES + STG_BYTES + 256 + 1024;
 
 __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sS = base;
-  const uint32_t sBar = base + STAGES * GR_STAGE_BYTES;
+  const uint32_t sStg = base + STAGES * GR_STAGE_BYTES;
+  const uint32_t sBar = sStg + STG_BYTES;
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tfull = sBar + 16 * STAGES;
   const uint32_t s_tmem_ptr = bar_tfull + 8;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -480,16 +530,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcAr
   } else {
     mbar_wait(bar_tfull, 0);
     tc_fence_after();
-    const int row = warp * 32 + lane;                            // row of C = column of A
-    float* dst = p.partial + static_cast<size_t>(blockIdx.x) * TILE * TILE + row * TILE;
+    float* dst = p.partial + static_cast<size_t>(blockIdx.x) * TILE * TILE;      // row of C = column of A
+    const uint32_t stg = sStg + warp * (32 * STG_PITCH * 4);
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
       uint32_t r[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cc * 32, r);
+      uint4 o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        st4(dst + cc * 32 + 4 * j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+      for (int j = 0; j < 8; ++j) o[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      store_block_coalesced(stg, o, lane, dst, TILE, warp * 32, TILE, cc * 32, TILE);
     }
   }
   tc_fence_before();
@@ -536,9 +586,32 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
   uint32_t* img = static_cast<uint32_t*>(workspace);
   tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, n, k, img);
   CGCN_TRY(check_launch("tc_prep_b_kernel"));
-  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rowscale_rowptr, rowscale_group, n, k};
+  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rowscale_rowptr, rowscale_group, n, k, nullptr};
   const int64_t tiles = (m + tc::TILE - 1) / tc::TILE;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  static const bool trace = getenv("CGCN_TC_TRACE") != nullptr;
+  if (trace) {                                                  // developer aid: synchronous, prints CTA 0's timeline
+    long long* d = nullptr;
+    CGCN_CUDA(cudaMalloc(&d, 7 * 64 * sizeof(long long)));
+    CGCN_CUDA(cudaMemset(d, 0, 7 * 64 * sizeof(long long)));
+    p.trace = d;
+    tc::gemm_rowpanel_tc_kernel<<<grid, tc::THREADS, tc::RP_SMEM, stream>>>(p);
+    CGCN_CUDA(cudaStreamSynchronize(stream));
+    long long h[7 * 64];
+    CGCN_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    static const char* names[7] = {"prod empty-wait done", "prod stores done", "prod arrived", "mma full-wait done",
+                                   "mma issued+commit", "epi tfull-wait done", "epi stores done"};
+    long long t0 = 0;
+    for (int i = 0; i < 7 * 64; ++i) if (h[i] && (t0 == 0 || h[i] < t0)) t0 = h[i];
+    fprintf(stderr, "[tc trace] m=%lld tiles=%lld grid=%d\n", (long long)m, (long long)tiles, grid);
+    for (int r = 0; r < 7; ++r) {
+      fprintf(stderr, "  %-22s", names[r]);
+      for (int i = 0; i < 32; ++i) if (h[r * 64 + i]) fprintf(stderr, " %6lld", h[r * 64 + i] - t0);
+      fprintf(stderr, "\n");
+    }
+    return check_launch("gemm_rowpanel_tc_kernel");
+  }
   tc::gemm_rowpanel_tc_kernel<<<grid, tc::THREADS, tc::RP_SMEM, stream>>>(p);
   return check_launch("gemm_rowpanel_tc_kernel");
 }

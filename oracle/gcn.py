@@ -135,8 +135,9 @@ def finetune_epoch(model: ChromeGCNOracle, chrom_feature_dict: Dict[str, Dict[st
     train = split == "train"
     model.train(train)
     preds, targs, total = [], [], 0.0
+    dtype = next(model.parameters()).dtype
     for chrom, feats in chrom_feature_dict.items():
-        adj = coo_adjacency(*graphs[chrom])
+        adj = coo_adjacency(*graphs[chrom], dtype=dtype)
         if train:
             loss, prob, _, _ = chromosome_step(model, feats["forward"], feats["backward"], feats["target"],
                                                adj, optimizer, True, input_grads=True)
