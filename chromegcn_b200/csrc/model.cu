@@ -7,6 +7,7 @@
 //   d loss / d W = (A_hat x)^T (d loss / d y)
 // SpMM-free and lets the first layer skip its backward SpMM when nobody needs d loss / d x_in.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -67,10 +68,16 @@ int sm_count() {
 }
 
 // ---- dense dispatch
+static thread_local int tls_rp_ordinal = 0, tls_gr_ordinal = 0;   // developer aid (CGCN_TC_MASK_RP / _GR bitmasks)
 int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                            int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
                            int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  const bool tc_ok = tc_rowpanel_supported(lda, ldc, n, k, A, C) && ws != nullptr && ws_bytes >= tc_workspace_bytes();
+  static const char* dis = getenv("CGCN_TC_DISABLE");          // developer aid: "rowpanel", "gram" or "rowscale"
+  bool tc_ok = tc_rowpanel_supported(lda, ldc, n, k, A, C) && ws != nullptr && ws_bytes >= tc_workspace_bytes();
+  if (dis && (strstr(dis, "rowpanel") || (strstr(dis, "rowscale") && rowscale_rowptr) || (strstr(dis, "head") && (n != 128 || k != 128)))) tc_ok = false;
+  static const char* mask_s = getenv("CGCN_TC_MASK_RP");
+  if (mask_s && !((atoi(mask_s) >> tls_rp_ordinal) & 1)) tc_ok = false;
+  ++tls_rp_ordinal;
   if (impl == 2 && !tc_ok) {
     set_error("cgcn_gemm_rowpanel: tcgen05 path needs n, k <= 128, 16-byte aligned rows of a multiple of 4 floats and a workspace");
     return CGCN_ERR_INVALID;
@@ -83,7 +90,12 @@ int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_tr
 
 int gemm_gram_dispatch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
                        int ka, int nb, int accumulate, int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  const bool tc_ok = tc_gram_supported(lda, ldb, ka, nb, A, B);
+  static const char* dis = getenv("CGCN_TC_DISABLE");
+  bool tc_ok = tc_gram_supported(lda, ldb, ka, nb, A, B);
+  if (dis && (strstr(dis, "gram") || (strstr(dis, "head") && (ka != 128 || nb != 128)))) tc_ok = false;
+  static const char* mask_s = getenv("CGCN_TC_MASK_GR");
+  if (mask_s && !((atoi(mask_s) >> tls_gr_ordinal) & 1)) tc_ok = false;
+  ++tls_gr_ordinal;
   if (impl == 2 && !tc_ok) {
     set_error("cgcn_gemm_gram: tcgen05 path needs ka, nb <= 128 and 16-byte aligned rows of a multiple of 4 floats");
     return CGCN_ERR_INVALID;
@@ -181,6 +193,7 @@ int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, 
 int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, float* db, float* dwg, float* dbg, cudaStream_t stream);
 
 static int model_forward(const cgcn_model* m) {
+  tls_rp_ordinal = tls_gr_ordinal = 0;
   CGCN_TRY(validate(m, false));
   cudaStream_t st = static_cast<cudaStream_t>(m->stream);
   const int n = m->graph.n, d = m->d, S = m->strands, C = m->nclass, L = m->layers;
