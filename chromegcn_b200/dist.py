@@ -112,6 +112,14 @@ def allgather_panel(local: torch.Tensor, parts: Sequence[Tuple[int, int]], out: 
     if world == 1:
         out.copy_(local)
         return out
-    chunks = [out[b:e] for b, e in parts]
-    dist.all_gather(chunks, local.contiguous(), group=group)
+    # blocks may differ by one row: gather fixed-size padded blocks, then drop the padding
+    rows_max = max(e - b for b, e in parts)
+    rank = dist.get_rank(group)
+    b0, e0 = parts[rank]
+    send = torch.zeros(rows_max, width, dtype=local.dtype, device=local.device)
+    send[: e0 - b0] = local
+    recv = torch.empty(world, rows_max, width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv.view(world * rows_max, width), send, group=group)
+    for r, (b, e) in enumerate(parts):
+        out[b:e] = recv[r, : e - b]
     return out
