@@ -35,6 +35,9 @@ class FlatParams:
         self.flat_grad: Optional[torch.Tensor] = None
         self.offsets: Dict[str, int] = {}
         self.total = 0
+        self._plist = None
+        self._named = []
+        self._views_cache: Dict = {}
 
     def _layout(self, params: Dict[str, torch.nn.Parameter], names: List[str]):
         off, offsets = 0, {}
@@ -43,7 +46,14 @@ class FlatParams:
             off += (params[k].numel() + _SLOT - 1) // _SLOT * _SLOT
         return offsets, off
 
-    def ensure(self) -> "FlatParams":
+    def ensure(self, full: bool = True) -> "FlatParams":
+        """`full=False` is the per-step fast path: only checks that the cached parameter objects still
+        point into the flat buffer (a dozen `data_ptr()` calls)."""
+        if not full and self.flat is not None and self._plist is not None:
+            base = self.flat.data_ptr()
+            if all(p.data_ptr() == base + 4 * off for p, off in self._plist):
+                self.attach_grads()
+                return self
         names = self.model._param_names()
         params = dict(self.model.named_parameters())
         dev = params[names[0]].device
@@ -62,28 +72,37 @@ class FlatParams:
                 p.data = view
             self.flat, self.offsets, self.total = flat, offsets, total
             self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            self._views_cache = {}
+        self._plist = [(params[k], offsets[k]) for k in names]
+        self._named = [(k, params[k]) for k in names]
         self.attach_grads()
         return self
 
     def attach_grads(self) -> None:
-        params = dict(self.model.named_parameters())
-        for k, off in self.offsets.items():
-            p = params[k]
-            want = self.flat_grad[off: off + p.numel()].view(p.shape)
-            if p.grad is None or p.grad.data_ptr() != want.data_ptr():
-                p.grad = want
+        for k, p in self._named:
+            off = self.offsets[k]
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                view = self.flat_grad[off: off + p.numel()].view(p.shape)
+                if p.grad is not None and p.grad.shape == view.shape:
+                    view.copy_(p.grad)           # gradients autograd produced through the module API
+                p.grad = view
 
     def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
-        params = dict(self.model.named_parameters())
-        return {k: flat[off: off + params[k].numel()].view(params[k].shape) for k, off in self.offsets.items()}
+        key = flat.data_ptr()
+        v = self._views_cache.get(key)
+        if v is None:
+            v = {k: flat[self.offsets[k]: self.offsets[k] + p.numel()].view(p.shape) for k, p in self._named}
+            self._views_cache[key] = v
+        return v
 
 
-def flat_params(model: ChromeGCN) -> FlatParams:
+def flat_params(model: ChromeGCN, full: bool = True) -> FlatParams:
     st = getattr(model, "_flat_state", None)
     if st is None:
         st = FlatParams(model)
         object.__setattr__(model, "_flat_state", st)
-    return st.ensure()
+        full = True
+    return st.ensure(full)
 
 
 class ChromosomeEngine:
@@ -118,7 +137,7 @@ class ChromosomeEngine:
         valid until the next call."""
         lib = _lib.load()
         model = self.model
-        fp = flat_params(model)
+        fp = flat_params(model, full=False)
         S = self.strands
         n, d = panel.shape[0], panel.shape[-1]
         nclass, layers = model.out.out_features, model.num_layers

@@ -70,11 +70,41 @@ def graphs_for(opt, split: str, chroms, sizes, device) -> Dict[str, HiCGraph]:
     return out
 
 
+_TARGETS: Dict = {}          # (id(dict), data_ptrs) -> concatenated CPU targets (they never change between epochs)
+_STAGING: Dict = {}          # (device, slot) -> persistent device staging buffers of the H2D pipeline
+
+
+def _staging(device, slot: int, n: int, d: int, nclass: int):
+    key = (str(device), slot)
+    cur = _STAGING.get(key)
+    if cur is None or cur[0].shape[0] < n or cur[0].shape[1] != d or cur[2].shape[1] != nclass:
+        rows = max(n, cur[0].shape[0] if cur is not None and cur[0].shape[1] == d else 0)
+        cur = (torch.empty(rows, d, dtype=torch.float32, device=device), torch.empty(rows, d, dtype=torch.float32, device=device),
+               torch.empty(rows, nclass, dtype=torch.float32, device=device))
+        _STAGING[key] = cur
+    return cur[0][:n], cur[1][:n], cur[2][:n]
+
+
+def _all_targets(chrom_feature_dict, chroms):
+    key = (id(chrom_feature_dict), tuple(chrom_feature_dict[c]["target"].data_ptr() for c in chroms))
+    t = _TARGETS.get(key)
+    if t is None:
+        t = (torch.cat([chrom_feature_dict[c]["target"].detach().cpu().float() for c in chroms], 0)
+             if chroms else torch.Tensor())
+        if len(_TARGETS) > 8:
+            _TARGETS.clear()
+        _TARGETS[key] = t
+    return t
+
+
 def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoch, data_dict, opt, split):
+    from . import ops
+    from .engine import flat_params
     device = _lib.require_cuda(next(ChromeModel.parameters()).device)
     train = split == "train"
     ChromeModel.train() if train else ChromeModel.eval()
     engine = engine_for(ChromeModel)
+    flat_params(ChromeModel, full=True)          # once per pass; the per-chromosome steps use the fast check
     chroms = list(chrom_feature_dict.keys())
     sizes = {c: chrom_feature_dict[c]["forward"].size(0) for c in chroms}
     nclass = ChromeModel.out.out_features
@@ -83,29 +113,34 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
 
     total_rows = sum(sizes.values())
     main = torch.cuda.current_stream(device)
-    copy_stream = torch.cuda.Stream(device)
     with torch.cuda.device(device):
+        h2d = torch.cuda.Stream(device)
+        d2h = torch.cuda.Stream(device)
         all_preds_dev = torch.empty(total_rows, nclass, dtype=torch.float32, device=device)
+        all_preds = torch.empty(total_rows, nclass, dtype=torch.float32, pin_memory=True)
         losses_dev = torch.zeros(max(len(chroms), 1), dtype=torch.float32, device=device)
         staged = [None, None]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        done = torch.cuda.Event()
 
         def stage(k: int):
-            """Issue the H2D copies of chromosome k on the copy stream (slot k % 2)."""
+            """Issue the H2D copies of chromosome k on the copy stream into staging slot k % 2."""
             chrom = chroms[k]
             feats = chrom_feature_dict[chrom]
             rkey = (id(chrom_feature_dict), chrom, str(device))
             if resident and rkey in _RESIDENT:
                 staged[k % 2] = ("resident",) + _RESIDENT[rkey]
                 return
-            with torch.cuda.stream(copy_stream):
+            n, d = feats["forward"].shape
+            x_f, x_r, tgt = _staging(device, k % 2, n, d, nclass)
+            with torch.cuda.stream(h2d):
                 if k >= 2:
-                    copy_stream.wait_event(consumed[k % 2])
-                x_f = feats["forward"].to(device, dtype=torch.float32, non_blocking=True)
-                x_r = feats["backward"].to(device, dtype=torch.float32, non_blocking=True)
-                tgt = feats["target"].to(device, dtype=torch.float32, non_blocking=True)
-                ready[k % 2].record(copy_stream)
+                    h2d.wait_event(consumed[k % 2])          # the slot's previous tenant has been packed / consumed
+                x_f.copy_(feats["forward"], non_blocking=True)
+                x_r.copy_(feats["backward"], non_blocking=True)
+                tgt.copy_(feats["target"], non_blocking=True)
+                ready[k % 2].record(h2d)
             staged[k % 2] = ("fresh", x_f, x_r, tgt)
 
         if chroms:
@@ -115,32 +150,31 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
             if k + 1 < len(chroms):
                 stage(k + 1)
             item = staged[k % 2]
+            n = sizes[chrom]
             if item[0] == "resident":
                 panel, tgt = item[1], item[2]
             else:
                 main.wait_event(ready[k % 2])
                 _, x_f, x_r, tgt = item
-                for t in (x_f, x_r, tgt):
-                    t.record_stream(main)
                 if resident:
-                    from . import ops
                     panel = ops.interleave_strands([x_f, x_r])
+                    tgt = tgt.clone()
                     _RESIDENT[(id(chrom_feature_dict), chrom, str(device))] = (panel, tgt)
                 else:
                     panel = engine.pack(x_f, x_r)
-            n = sizes[chrom]
             if train:
                 optimizer.zero_grad()                                        # finetune.py:39
             engine.run(graphs[chrom], panel, tgt, all_preds_dev[row: row + n], losses_dev[k: k + 1], train)
             if train:
                 optimizer.step()                                             # finetune.py:49
             consumed[k % 2].record(main)
+            # predictions of this chromosome go home while the next one computes (finetune.py:52)
+            d2h.wait_event(consumed[k % 2])
+            with torch.cuda.stream(d2h):
+                all_preds[row: row + n].copy_(all_preds_dev[row: row + n], non_blocking=True)
             row += n
-
-        all_preds = torch.empty(total_rows, nclass, dtype=torch.float32, pin_memory=True)
-        all_preds.copy_(all_preds_dev, non_blocking=True)
+        done.record(d2h)
         losses = losses_dev.cpu()                                            # the one sync of the split
+        done.synchronize()
     total_loss = float(losses.double().sum().item()) if chroms else 0
-    all_targets = (torch.cat([chrom_feature_dict[c]["target"].detach().cpu().float() for c in chroms], 0)
-                   if chroms else torch.Tensor())
-    return all_preds, all_targets, total_loss
+    return all_preds, _all_targets(chrom_feature_dict, chroms), total_loss

@@ -27,11 +27,11 @@ class _FlatOptimizer(torch.optim.Optimizer):
             self._flat_buffers[name] = b
         return b
 
-    def zero_grad(self, set_to_none: bool = False):
-        # the fused backward overwrites every gradient; keep the flat views attached
-        fp = flat_params(self.model)
+    def zero_grad(self, set_to_none: bool = True):
+        # the fused backward overwrites (never accumulates into) every gradient, so there is nothing to
+        # clear on the hot path; an explicit zero_grad(set_to_none=False) still zeroes the flat buffer
         if not set_to_none:
-            fp.flat_grad.zero_()
+            flat_params(self.model, full=False).flat_grad.zero_()
 
     def state_dict(self):
         sd = super().state_dict()
@@ -54,7 +54,7 @@ class FlatSGD(_FlatOptimizer):
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
-        fp = flat_params(self.model)
+        fp = flat_params(self.model, full=False)
         buf = self._buffer("momentum", fp.flat)
         ops.sgd_step(fp.flat, fp.flat_grad, buf, g["lr"], g["momentum"], g["weight_decay"], self.grad_scale)
 
@@ -68,7 +68,7 @@ class FlatAdam(_FlatOptimizer):
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
-        fp = flat_params(self.model)
+        fp = flat_params(self.model, full=False)
         m = self._buffer("exp_avg", fp.flat)
         v = self._buffer("exp_avg_sq", fp.flat)
         self._steps += 1
