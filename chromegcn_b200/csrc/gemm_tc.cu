@@ -630,7 +630,9 @@ int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float
     CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GR_SMEM));
     attr_set = true;
   }
-  int64_t rows = gram_rows_per_cta(m);
+  // one CTA per SM (the kernel owns the whole shared memory): a single wave, <= #SM partial tiles
+  int64_t rows = (m + sm_count() - 1) / sm_count();
+  if (rows < 256) rows = 256;
   rows = (rows + tc::KCH - 1) / tc::KCH * tc::KCH;
   const int parts = static_cast<int>((m + rows - 1) / rows);
   tc::GramTcArgs p{A, lda, B, ldb, m, rows, static_cast<float*>(workspace), ka, nb};

@@ -66,7 +66,7 @@ __device__ __forceinline__ void gather_range(const int32_t* __restrict__ colidx,
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(SPMM_WARPS * 32)
+__global__ void __launch_bounds__(SPMM_WARPS * 32, (VEC <= 2) ? 5 : 2)
 spmm_pattern_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
                     const float* __restrict__ x, float* __restrict__ out, int scale_mode,
                     const float* __restrict__ residual) {
