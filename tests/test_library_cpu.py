@@ -82,3 +82,15 @@ def test_reference_state_dict_loads():
     m = ChromeGCN(128, 128, 11, 0.2, True, 2)
     assert float(m.GC1.bias.abs().max()) == 0.0
     assert abs(float(m.GC1.weight.std()) - 0.02 * (2.0 / 256) ** 0.5) < 2e-4
+
+
+def test_cli_flags_match_reference():
+    """config_args.py:4-54: the single-dash flags of the README GCN recipe parse to the reference's derived fields."""
+    import argparse
+    from chromegcn_b200.config_args import config_args, get_args
+    argv = ("-load_pretrained -chrome_model gcn -gate -gcn_layers 2 -adj_type hic -hicnorm SQRTVC -hicsize 500000 "
+            "-optim sgd -lr 0.25 -gcn_dropout 0.2 -epochs 1000 -dataroot /data -results_dir /res").split()
+    opt = config_args(get_args(argparse.ArgumentParser(), argv))
+    assert opt.graph_root == "/data/GM12878/1000/hic" and opt.batch_size == 512 and opt.hicsize == "500000"
+    assert opt.model_name.endswith(".finetune.lr2_002.gcndrop_20.adam.gcn.layers_2.gate.adj_hic.norm_SQRTVC")
+    assert opt.model_name.startswith("/res/GM12878/graph.expecto.128.bsz_64.loss_ce.sgd.lr_25.drop_10_10")
