@@ -11,7 +11,7 @@ from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libchromegcn.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ChromeGCNNativeError(RuntimeError):
@@ -19,7 +19,8 @@ class ChromeGCNNativeError(RuntimeError):
 
 
 class Graph(C.Structure):
-    _fields_ = [("n", C.c_int32), ("nnz", C.c_int32), ("rowptr", C.c_void_p), ("colidx", C.c_void_p)]
+    _fields_ = [("n", C.c_int32), ("nnz", C.c_int32), ("rowptr", C.c_void_p), ("colidx", C.c_void_p),
+                ("vals", C.c_void_p), ("row_inv", C.c_void_p)]
 
 
 class Params(C.Structure):
@@ -60,7 +61,7 @@ PROTOTYPES = {
     "cgcn_coo_to_pattern_workspace_bytes": (C.c_int, [_I64, _I64, C.POINTER(_SZ)]),
     "cgcn_coo_to_pattern": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, C.POINTER(_I32), _P, _SZ, _P]),
     "cgcn_spmm": (C.c_int, [C.POINTER(Graph), _P, _P, _I32, _I32, _P, _P]),
-    "cgcn_gemm_rowpanel": (C.c_int, [_P, _I64, _P, _I32, _P, _P, _I64, _I64, _I32, _I32, _P, _I32, _I32, _P, _SZ, _P]),
+    "cgcn_gemm_rowpanel": (C.c_int, [_P, _I64, _P, _I32, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _I32, _I32, _P, _SZ, _P]),
     "cgcn_gemm_gram_workspace_bytes": (_SZ, [_I64]),
     "cgcn_gemm_gram": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P, _SZ, _P]),
     "cgcn_model_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32, _I32]),

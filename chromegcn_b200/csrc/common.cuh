@@ -81,6 +81,11 @@ __device__ __forceinline__ float inv_degree(const int32_t* __restrict__ rowptr, 
   return deg > 0 ? __fdiv_rn(1.0f, static_cast<float>(deg)) : 0.0f;
 }
 
+// 1/deg from the pattern, or the stored 1/rowsum of a weighted graph
+__device__ __forceinline__ float row_scale(const int32_t* __restrict__ rowptr, const float* __restrict__ row_inv, int row) {
+  return row_inv != nullptr ? __ldg(row_inv + row) : inv_degree(rowptr, row);
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // Philox4x32-10: counter-based, so the dropout keep-mask is a pure function of

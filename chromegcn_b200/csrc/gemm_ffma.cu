@@ -28,6 +28,7 @@ struct RowPanelArgs {
   int64_t m;
   int n, k;
   const int32_t* rowscale_rowptr;
+  const float* rowscale_inv;
   int rowscale_group;
   int a_vec, c_vec;              // 128-bit access legal on A rows / C rows
 };
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_rowpanel_kernel(const RowPan
       const int64_t grow = row0 + r;
       if (grow >= p.m) continue;
       float s = 1.0f;
-      if (p.rowscale_rowptr != nullptr) s = inv_degree(p.rowscale_rowptr, static_cast<int>(grow / p.rowscale_group));
+      if (p.rowscale_rowptr != nullptr || p.rowscale_inv != nullptr)
+        s = row_scale(p.rowscale_rowptr, p.rowscale_inv, static_cast<int>(grow / p.rowscale_group));
       float* dst = p.C + grow * p.ldc;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -170,14 +172,14 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_rowpanel_kernel(const RowPan
 }
 
 int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
-                       int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                       int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
                        cudaStream_t stream) {
   CGCN_REQUIRE(A && B && C, "cgcn_gemm_rowpanel: null operand");
   CGCN_REQUIRE(n >= 1 && n <= GB && k >= 1 && k <= GB, "cgcn_gemm_rowpanel: n=%d k=%d must be in [1,128]", n, k);
   CGCN_REQUIRE(lda >= k && ldc >= n, "cgcn_gemm_rowpanel: leading dimension too small");
-  CGCN_REQUIRE(rowscale_rowptr == nullptr || rowscale_group >= 1, "cgcn_gemm_rowpanel: rowscale_group");
+  CGCN_REQUIRE((rowscale_rowptr == nullptr && rowscale_inv == nullptr) || rowscale_group >= 1, "cgcn_gemm_rowpanel: rowscale_group");
   if (m <= 0) return CGCN_OK;
-  RowPanelArgs p{A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_group, 0, 0};
+  RowPanelArgs p{A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, 0, 0};
   p.a_vec = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
   p.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
   const int k_pad = (k + GBK - 1) / GBK * GBK;

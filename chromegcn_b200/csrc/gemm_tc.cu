@@ -203,6 +203,7 @@ struct RowPanelTcArgs {
   int64_t ldc;
   int64_t m;
   const int32_t* rowscale_rowptr;
+  const float* rowscale_inv;
   int rowscale_group;
   int n_valid, k_valid;        // <= 128; A rows hold round_up(k_valid, 4) readable floats, C rows round_up(n_valid, 4) writable
   long long* trace;            // developer aid (CGCN_TC_TRACE=1): per-role clock64() stamps of CTA 0, else NULL
@@ -362,8 +363,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
       tc_fence_after();
       const int64_t grow = tile * TILE + warp * 32 + lane;
       float scale = 1.0f;
-      if (p.rowscale_rowptr != nullptr && grow < p.m)
-        scale = inv_degree(p.rowscale_rowptr, static_cast<int>(grow / p.rowscale_group));
+      if ((p.rowscale_rowptr != nullptr || p.rowscale_inv != nullptr) && grow < p.m)
+        scale = row_scale(p.rowscale_rowptr, p.rowscale_inv, static_cast<int>(grow / p.rowscale_group));
       const uint32_t stg = sStg + warp * (32 * STG_PITCH * 4);
       const int n_store = (p.n_valid + 3) & ~3;
 #pragma unroll 1
@@ -567,7 +568,7 @@ bool tc_gram_supported(int64_t lda, int64_t ldb, int ka, int nb, const void* A, 
 size_t tc_workspace_bytes() { return tc::RP_B_BYTES + 256; }
 
 int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
-                     int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                     int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   CGCN_REQUIRE(A && B && C, "cgcn_gemm_rowpanel: null operand");
   CGCN_REQUIRE(tc_rowpanel_supported(lda, ldc, n, k, A, C),
@@ -586,7 +587,7 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
   uint32_t* img = static_cast<uint32_t*>(workspace);
   tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, n, k, img);
   CGCN_TRY(check_launch("tc_prep_b_kernel"));
-  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rowscale_rowptr, rowscale_group, n, k, nullptr};
+  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rowscale_rowptr, rowscale_inv, rowscale_group, n, k, nullptr};
   const int64_t tiles = (m + tc::TILE - 1) / tc::TILE;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   static const bool trace = getenv("CGCN_TC_TRACE") != nullptr;

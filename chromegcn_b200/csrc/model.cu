@@ -19,13 +19,13 @@ namespace cgcn {
 int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int scale_mode, const float* residual,
                 cudaStream_t stream);
 int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
-                       int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                       int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
                        cudaStream_t stream);
 int gemm_gram_ffma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
                    int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gram_workspace_bytes(int64_t m);
 int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
-                     int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                     int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
                  int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -70,7 +70,7 @@ int sm_count() {
 // ---- dense dispatch
 static thread_local int tls_rp_ordinal = 0, tls_gr_ordinal = 0;   // developer aid (CGCN_TC_MASK_RP / _GR bitmasks)
 int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
-                           int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, int rowscale_group,
+                           int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
                            int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
   static const char* dis = getenv("CGCN_TC_DISABLE");          // developer aid: "rowpanel", "gram" or "rowscale"
   bool tc_ok = tc_rowpanel_supported(lda, ldc, n, k, A, C) && ws != nullptr && ws_bytes >= tc_workspace_bytes();
@@ -83,9 +83,9 @@ int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_tr
     return CGCN_ERR_INVALID;
   }
   if (impl == 2 || (impl == 0 && tc_ok))
-    return gemm_rowpanel_tc(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_group, ws, ws_bytes,
+    return gemm_rowpanel_tc(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, ws, ws_bytes,
                             stream);
-  return gemm_rowpanel_ffma(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_group, stream);
+  return gemm_rowpanel_ffma(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, stream);
 }
 
 int gemm_gram_dispatch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
@@ -157,6 +157,7 @@ static WsLayout make_layout(int n, int d, int nclass, int layers, int strands) {
 static int validate(const cgcn_model* m, bool backward) {
   CGCN_REQUIRE(m != nullptr, "cgcn_model: null");
   CGCN_REQUIRE(m->graph.n >= 1 && m->graph.rowptr && m->graph.colidx, "cgcn_model: bad graph");
+  CGCN_REQUIRE((m->graph.vals == nullptr) == (m->graph.row_inv == nullptr), "cgcn_model: weighted graphs need vals and row_inv");
   CGCN_REQUIRE(m->d == 128, "cgcn_model: d=%d (the model path supports d = 128, the width main.py:62 fixes)", m->d);
   CGCN_REQUIRE(m->nclass >= 1 && m->nclass <= 128, "cgcn_model: nclass=%d must be in [1,128]", m->nclass);
   CGCN_REQUIRE(m->layers == 1 || m->layers == 2, "cgcn_model: layers=%d", m->layers);
@@ -209,7 +210,7 @@ static int model_forward(const cgcn_model* m) {
     CGCN_TRY(spmm_launch(&m->graph, xin, ws + lay.ax[l], W, 1, nullptr, st));
     // y = ax W + b                                   (torch.mm + bias, models/SubLayers.py:43,50)
     CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.ax[l], d, m->params.gc_w[l], 0, m->params.gc_b[l], ws + lay.z[l], d, M, d, d,
-                                    nullptr, 1, m->gemm_impl, tcws, lay.tc_bytes, st));
+                                    nullptr, nullptr, 1, m->gemm_impl, tcws, lay.tc_bytes, st));
     // z = tanh(y); g = sigmoid(W z); x' = (1-g) x + g z; dropout between the layers
     //                                                (models/ChromeModels.py:38-42 / 44-46)
     GateFwdArgs a{};
@@ -246,7 +247,7 @@ static int model_forward(const cgcn_model* m) {
   CGCN_TRY(bn_apply_launch(b, st));
   // out = hb Wout^T + bout                           (models/ChromeModels.py:51)
   const int ldo = m->out_ld > 0 ? m->out_ld : C;
-  CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.hb, d, m->params.out_w, 1, m->params.out_b, m->out, ldo, M, C, d, nullptr, 1,
+  CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.hb, d, m->params.out_w, 1, m->params.out_b, m->out, ldo, M, C, d, nullptr, nullptr, 1,
                                   m->gemm_impl, tcws, lay.tc_bytes, st));
   return CGCN_OK;
 }
@@ -270,7 +271,7 @@ static int model_backward(const cgcn_model* m) {
   CGCN_TRY(gemm_gram_dispatch(m->out_grad, ldo, ws + lay.hb, d, m->grads.out_w, d, M, C, d, 0, m->gemm_impl, gram_ws,
                               lay.gram_bytes, st));
   CGCN_TRY(colsum_launch(m->out_grad, M, C, ldo, m->grads.out_b, ws + lay.partial, st));
-  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, ldo, m->params.out_w, 0, nullptr, dA, d, M, d, C, nullptr, 1, m->gemm_impl,
+  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, ldo, m->params.out_w, 0, nullptr, dA, d, M, d, C, nullptr, nullptr, 1, m->gemm_impl,
                                   tcws, lay.tc_bytes, st));
   // BatchNorm backward sums
   {
@@ -321,7 +322,7 @@ static int model_backward(const cgcn_model* m) {
     if (!need_dx) break;
     // t = D^-1 (dy W^T)  ->  the panel that held `src` ; then dx = dxd + P t
     float* t = const_cast<float*>(src);
-    CGCN_TRY(gemm_rowpanel_dispatch(dy, d, m->params.gc_w[l], 1, nullptr, t, d, M, d, d, m->graph.rowptr, S, m->gemm_impl,
+    CGCN_TRY(gemm_rowpanel_dispatch(dy, d, m->params.gc_w[l], 1, nullptr, t, d, M, d, d, m->graph.rowptr, m->graph.row_inv, S, m->gemm_impl,
                                     tcws, lay.tc_bytes, st));
     float* dx = (l == 0) ? m->x_in_grad : dy;          // dy is dead after the two contractions above
     CGCN_TRY(spmm_launch(&m->graph, t, dx, W, 0, dxd, st));
@@ -382,9 +383,9 @@ extern "C" int cgcn_train_step(const cgcn_model* m, const float* target, float* 
 
 extern "C" int cgcn_gemm_rowpanel(const float* A, int64_t lda, const float* B, int32_t b_transposed, const float* bias,
                                   float* C, int64_t ldc, int64_t m, int32_t n, int32_t k,
-                                  const int32_t* rowscale_rowptr, int32_t rowscale_group, int32_t gemm_impl,
+                                  const int32_t* rowscale_rowptr, const float* rowscale_inv, int32_t rowscale_group, int32_t gemm_impl,
                                   void* workspace, size_t workspace_bytes, cgcn_stream_t stream) {
-  return gemm_rowpanel_dispatch(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_group,
+  return gemm_rowpanel_dispatch(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group,
                                 gemm_impl, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

@@ -21,20 +21,24 @@ namespace cgcn {
 constexpr int SPMM_WARPS = 8;
 constexpr int LONG_ROW = 512;
 
-template <int VEC>
-__device__ __forceinline__ void gather_range(const int32_t* __restrict__ colidx, const float* __restrict__ x, int begin,
-                                             int end, int lane, float4 (&acc)[VEC]) {
+template <int VEC, bool WEIGHTED>
+__device__ __forceinline__ void gather_range(const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                             const float* __restrict__ x, int begin, int end, int lane, float4 (&acc)[VEC]) {
   constexpr int UNROLL = (VEC >= 8) ? 1 : (8 / VEC);
   constexpr size_t PITCH = static_cast<size_t>(VEC) * 128;
   for (int base = begin; base < end; base += 32) {
     const int mine = (base + lane < end) ? __ldg(colidx + base + lane) : 0;
+    float wmine = 1.0f;
+    if (WEIGHTED) wmine = (base + lane < end) ? __ldg(vals + base + lane) : 0.0f;
     const int cnt = min(32, end - base);
     int k = 0;
     for (; k + UNROLL <= cnt; k += UNROLL) {
       float4 v[UNROLL][VEC];
+      float w[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         const int c = __shfl_sync(0xffffffffu, mine, k + u);
+        w[u] = WEIGHTED ? __shfl_sync(0xffffffffu, wmine, k + u) : 1.0f;
         const float* p = x + static_cast<size_t>(c) * PITCH + lane * 4;
 #pragma unroll
         for (int q = 0; q < VEC; ++q) v[u][q] = ldg4(p + q * 128);
@@ -43,33 +47,42 @@ __device__ __forceinline__ void gather_range(const int32_t* __restrict__ colidx,
       for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
-          acc[q].x += v[u][q].x;
-          acc[q].y += v[u][q].y;
-          acc[q].z += v[u][q].z;
-          acc[q].w += v[u][q].w;
+          if (WEIGHTED) {
+            acc[q].x = fmaf(w[u], v[u][q].x, acc[q].x);
+            acc[q].y = fmaf(w[u], v[u][q].y, acc[q].y);
+            acc[q].z = fmaf(w[u], v[u][q].z, acc[q].z);
+            acc[q].w = fmaf(w[u], v[u][q].w, acc[q].w);
+          } else {
+            acc[q].x += v[u][q].x;
+            acc[q].y += v[u][q].y;
+            acc[q].z += v[u][q].z;
+            acc[q].w += v[u][q].w;
+          }
         }
       }
     }
     for (; k < cnt; ++k) {
       const int c = __shfl_sync(0xffffffffu, mine, k);
+      const float w1 = WEIGHTED ? __shfl_sync(0xffffffffu, wmine, k) : 1.0f;
       const float* p = x + static_cast<size_t>(c) * PITCH + lane * 4;
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
         const float4 v = ldg4(p + q * 128);
-        acc[q].x += v.x;
-        acc[q].y += v.y;
-        acc[q].z += v.z;
-        acc[q].w += v.w;
+        acc[q].x = fmaf(w1, v.x, acc[q].x);
+        acc[q].y = fmaf(w1, v.y, acc[q].y);
+        acc[q].z = fmaf(w1, v.z, acc[q].z);
+        acc[q].w = fmaf(w1, v.w, acc[q].w);
       }
     }
   }
 }
 
-template <int VEC>
+template <int VEC, bool WEIGHTED>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, (VEC <= 2) ? 5 : 2)
 spmm_pattern_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
                     const float* __restrict__ x, float* __restrict__ out, int scale_mode,
-                    const float* __restrict__ residual) {
+                    const float* __restrict__ residual, const float* __restrict__ vals,
+                    const float* __restrict__ row_inv) {
   constexpr size_t PITCH = static_cast<size_t>(VEC) * 128;
   __shared__ float4 red[SPMM_WARPS][VEC][32];
   const int lane = threadIdx.x & 31;
@@ -87,8 +100,9 @@ spmm_pattern_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
     float4 acc[VEC];
 #pragma unroll
     for (int q = 0; q < VEC; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gather_range<VEC>(colidx, x, start, end, lane, acc);
-    const float s = (scale_mode == 1 && deg > 0) ? __fdiv_rn(1.0f, static_cast<float>(deg)) : 1.0f;
+    gather_range<VEC, WEIGHTED>(colidx, vals, x, start, end, lane, acc);
+    const float s = (scale_mode != 1) ? 1.0f
+                    : (WEIGHTED ? __ldg(row_inv + row) : (deg > 0 ? __fdiv_rn(1.0f, static_cast<float>(deg)) : 1.0f));
     float* o = out + static_cast<size_t>(row) * PITCH + lane * 4;
 #pragma unroll
     for (int q = 0; q < VEC; ++q) {
@@ -118,12 +132,12 @@ spmm_pattern_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
     float4 acc[VEC];
 #pragma unroll
     for (int q = 0; q < VEC; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gather_range<VEC>(colidx, x, b, e, lane, acc);
+    gather_range<VEC, WEIGHTED>(colidx, vals, x, b, e, lane, acc);
 #pragma unroll
     for (int q = 0; q < VEC; ++q) red[warp][q][lane] = acc[q];
     __syncthreads();
     if (warp == 0) {
-      const float s = (scale_mode == 1) ? __fdiv_rn(1.0f, static_cast<float>(ldeg)) : 1.0f;
+      const float s = (scale_mode != 1) ? 1.0f : (WEIGHTED ? __ldg(row_inv + lrow) : __fdiv_rn(1.0f, static_cast<float>(ldeg)));
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
         float4 t = red[0][q][lane];
@@ -159,9 +173,16 @@ int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int 
   if (g->n <= 0) return CGCN_OK;
   const int vec = width / 128;
   const dim3 grid((g->n + SPMM_WARPS - 1) / SPMM_WARPS), block(SPMM_WARPS * 32);
-#define SPMM_CASE(V)                                                                                              \
-  case V:                                                                                                         \
-    spmm_pattern_kernel<V><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, x, out, scale_mode, residual); \
+  const bool weighted = g->vals != nullptr;
+  CGCN_REQUIRE(!weighted || g->row_inv != nullptr, "cgcn_spmm: weighted graph without row_inv");
+#define SPMM_CASE(V)                                                                                                  \
+  case V:                                                                                                             \
+    if (weighted)                                                                                                     \
+      spmm_pattern_kernel<V, true><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, x, out, scale_mode, residual, \
+                                                               g->vals, g->row_inv);                                 \
+    else                                                                                                              \
+      spmm_pattern_kernel<V, false><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, x, out, scale_mode,      \
+                                                                residual, nullptr, nullptr);                          \
     break;
   switch (vec) {
     SPMM_CASE(1)

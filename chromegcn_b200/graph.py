@@ -25,9 +25,12 @@ class HiCGraph:
     exact tensor the reference's `process_graph` would have produced.
     """
 
-    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, n: int, nnz: int, name: str = ""):
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, n: int, nnz: int, name: str = "",
+                 vals: Optional[torch.Tensor] = None, row_inv: Optional[torch.Tensor] = None):
         assert rowptr.dtype == torch.int32 and colidx.dtype == torch.int32 and rowptr.is_cuda and colidx.is_cuda
+        assert (vals is None) == (row_inv is None)
         self.rowptr, self.colidx, self.n, self.nnz, self.name = rowptr, colidx, int(n), int(nnz), name
+        self.vals, self.row_inv = vals, row_inv          # weighted graphs only (adj_type 'both')
 
     # -- torch-tensor look-alikes used by the reference's call sites
     def cuda(self, *a, **k):
@@ -52,7 +55,9 @@ class HiCGraph:
         return True
 
     def c_struct(self) -> _lib.Graph:
-        return _lib.Graph(self.n, self.nnz, self.rowptr.data_ptr(), self.colidx.data_ptr())
+        return _lib.Graph(self.n, self.nnz, self.rowptr.data_ptr(), self.colidx.data_ptr(),
+                          None if self.vals is None else self.vals.data_ptr(),
+                          None if self.row_inv is None else self.row_inv.data_ptr())
 
     def degrees(self) -> torch.Tensor:
         return (self.rowptr[1:] - self.rowptr[:-1])
@@ -62,7 +67,10 @@ class HiCGraph:
         row-major / ascending-column order, fp32 values `1/deg_i`, not coalesced."""
         deg = self.degrees().to(torch.int64)
         rows = torch.repeat_interleave(torch.arange(self.n, device=self.device), deg)
-        vals = (1.0 / deg.to(torch.float32))[rows]          # correctly rounded == float32(1/float64(deg))
+        if self.vals is not None:
+            vals = (self.vals[: self.nnz].double() * self.row_inv.double()[rows]).float()
+        else:
+            vals = (1.0 / deg.to(torch.float32))[rows]      # correctly rounded == float32(1/float64(deg))
         idx = torch.stack([rows, self.colidx[: self.nnz].to(torch.int64)])
         return torch.sparse_coo_tensor(idx, vals, (self.n, self.n), check_invariants=False)
 
@@ -144,6 +152,25 @@ class HiCGraph:
         return cls(rp, ci, n, nnz, name)
 
 
+def weighted_from_scipy(mat, device=None, name: str = "") -> HiCGraph:
+    """A weighted, SYMMETRIC, un-normalised scipy matrix (diagonal included) -> device graph that
+    aggregates with `D^-1 A` (`normalize`, utils/util_methods.py:99-106): raw weights + 1/rowsum."""
+    dev = _lib.require_cuda(device)
+    csr = mat.tocsr().astype(np.float64)
+    csr.sum_duplicates()
+    csr.sort_indices()
+    if (abs(csr - csr.T) > 0).nnz != 0:
+        raise NotImplementedError("weighted adjacency must be symmetric before normalisation (backward uses A = A^T)")
+    rowsum = np.asarray(csr.sum(1)).ravel()
+    with np.errstate(divide="ignore"):
+        r_inv = np.power(rowsum, -1.0)
+    r_inv[np.isinf(r_inv)] = 0.0                               # utils/util_methods.py:103
+    n = csr.shape[0]
+    return HiCGraph(torch.from_numpy(csr.indptr.astype(np.int32)).to(dev), torch.from_numpy(csr.indices.astype(np.int32)).to(dev),
+                    n, int(csr.nnz), name, torch.from_numpy(csr.data.astype(np.float32)).to(dev),
+                    torch.from_numpy(r_inv.astype(np.float32)).to(dev))
+
+
 def constant_band_pattern(constant_range: int, n: int):
     """Pattern of `create_constant_graph` (utils/util_methods.py:137-144): |i-j| <= range, i != j."""
     offs = np.arange(-constant_range, constant_range + 1)
@@ -162,8 +189,8 @@ def process_graph(adj_type, split_adj_dict_chrom, x_size, chrom, device=None) ->
 
     Same arguments; returns a `HiCGraph` (device CSR pattern of the row-normalised matrix) instead
     of a host-built torch sparse tensor.  `hic`, `constant` and `none` are mean aggregations over a
-    symmetric pattern and are supported; `both` (hic + band, not binarised: values vary inside a
-    row) is not on this path yet and raises."""
+    symmetric pattern; `both` (hic + band, not binarised: values vary inside a
+    row) runs on the weighted variant of the same kernels."""
     if adj_type == "hic":
         return HiCGraph.from_scipy(split_adj_dict_chrom[chrom], device, name=str(chrom))
     if adj_type == "constant":
@@ -174,5 +201,11 @@ def process_graph(adj_type, split_adj_dict_chrom, x_size, chrom, device=None) ->
         return HiCGraph.from_csr_pattern(np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32), device, False,
                                          name="none")
     if adj_type == "both":
-        raise NotImplementedError("adj_type 'both' needs the weighted-CSR path (values differ inside a row)")
+        # hic + band + I, NOT binarised (utils/util_methods.py:166-169): overlapping entries weigh 2
+        from scipy import sparse
+        n = int(x_size)
+        ip, ix = constant_band_pattern(7, n)
+        band = sparse.csr_matrix((np.ones(ix.shape[0]), ix, ip), shape=(n, n))
+        mat = split_adj_dict_chrom[chrom].tocsr() + band + sparse.eye(n, format="csr")
+        return weighted_from_scipy(mat, device, name=str(chrom) + "+band")
     raise ValueError("unknown adj_type %r" % (adj_type,))

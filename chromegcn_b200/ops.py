@@ -62,6 +62,7 @@ def gemm_rowpanel(a: torch.Tensor, b: torch.Tensor, b_transposed: bool = False, 
         _lib.check(lib.cgcn_gemm_rowpanel(a.data_ptr(), k, b.data_ptr(), int(b_transposed), _lib.ptr(bias_c),
                                           out.data_ptr(), n, m, n, k,
                                           rowscale_graph.rowptr.data_ptr() if rowscale_graph is not None else None,
+                                          _lib.ptr(rowscale_graph.row_inv) if rowscale_graph is not None else None,
                                           rowscale_group, impl, ws.data_ptr(), ws.numel(), _lib.current_stream()),
                    "cgcn_gemm_rowpanel")
     return out

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CGCN_ABI_VERSION 1
+#define CGCN_ABI_VERSION 2
 
 typedef void* cgcn_stream_t; /* cudaStream_t */
 
@@ -113,6 +113,12 @@ typedef struct cgcn_graph {
   int32_t nnz;           /* stored entries of bin(A+I) */
   const int32_t* rowptr; /* [n+1] */
   const int32_t* colidx; /* [nnz], ascending inside a row */
+  /* Weighted graphs (adj_type 'both', utils/util_methods.py:166-169: hic + band + I is NOT binarised, so
+   * values differ inside a row).  Both NULL = pattern-only mean aggregation (hic / constant / none).
+   * vals: the raw SYMMETRIC weights a_ij of the un-normalised matrix; row_inv: 1 / sum_j a_ij.
+   * Forward  A_hat x = row_inv_i * sum_j a_ij x_j ; backward  A_hat^T G = A (row_inv .* G). */
+  const float* vals;     /* [nnz] or NULL */
+  const float* row_inv;  /* [n] or NULL */
 } cgcn_graph;
 
 /*
@@ -120,6 +126,7 @@ typedef struct cgcn_graph {
  *   scale_mode 0: scale_i = 1           (backward: A_hat^T G = P (D^-1 G), D^-1 folded upstream)
  *   scale_mode 1: scale_i = 1/deg_i     (forward mean aggregation, torch.spmm(adj, .) of
  *                                        models/SubLayers.py:46 with adj = D^-1 bin(A+I))
+ * With g->vals the sum is weighted by a_ij and scale_i = g->row_inv[i].
  * width = floats per row (strands*d), a multiple of 128.  residual may be NULL.
  */
 int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, int32_t scale_mode,
@@ -132,12 +139,13 @@ int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, in
  * b_transposed 0: B is [k][n] row-major (torch.mm(input, weight), models/SubLayers.py:43);
  * b_transposed 1: B is [n][k] row-major (nn.Linear weight, models/ChromeModels.py:51).
  * bias [n] or NULL.  rowscale_rowptr: NULL, or the graph's rowptr: row r is scaled by
- * 1/deg(r / rowscale_group) (the D^-1 of A_hat^T applied to the input of the backward SpMM).
+ * 1/deg(r / rowscale_group) (the D^-1 of A_hat^T applied to the input of the backward SpMM);
+ * rowscale_inv: NULL, or the graph's row_inv (weighted graphs; takes precedence over rowscale_rowptr).
  * k, n <= 128.  The tcgen05 path needs lda, ldc multiples of 4 (rows padded to round_up(k|n, 4) floats).
  */
 int cgcn_gemm_rowpanel(const float* A, int64_t lda, const float* B, int32_t b_transposed, const float* bias,
                        float* C, int64_t ldc, int64_t m, int32_t n, int32_t k,
-                       const int32_t* rowscale_rowptr, int32_t rowscale_group,
+                       const int32_t* rowscale_rowptr, const float* rowscale_inv, int32_t rowscale_group,
                        int32_t gemm_impl, void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
 /*
  * C[ka x nb] (+)= sum_r A[r][0:ka] (x) B[r][0:nb]   (weight gradients X^T G: a reduction over

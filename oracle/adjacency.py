@@ -158,5 +158,35 @@ def pattern_with_selfloops(indptr, indices):
     return np.cumsum(rp).astype(np.int32), c.astype(np.int32)
 
 
+def process_graph_general(adj_type: str, indptr, indices, n: int):
+    """`process_graph` for every adj_type (utils/util_methods.py:146-180) as `(rows, cols, vals float32)` in
+    row-major / ascending-column order: 'hic' binarises A + I; 'constant' is the |i-j| <= 7 band + I;
+    'both' is A + band + I WITHOUT binarising (overlaps weigh 2); 'none' is I.  All row-normalised in
+    float64 (`normalize`, :99-106) and cast to float32 (:122)."""
+    from scipy import sparse
+    band = sparse.diags([np.ones(n - abs(k)) for k in range(-7, 8) if k != 0], [k for k in range(-7, 8) if k != 0],
+                        shape=(n, n), format="csr") if n > 7 else None
+    if adj_type == "hic":
+        return normalize_hic(indptr, indices, n)
+    if adj_type == "none":
+        mat = sparse.eye(n, format="csr")
+    elif adj_type == "constant":
+        mat = band + sparse.eye(n, format="csr")
+    elif adj_type == "both":
+        a = sparse.csr_matrix((np.ones(len(indices)), np.asarray(indices), np.asarray(indptr)), shape=(n, n))
+        mat = a + band + sparse.eye(n, format="csr")
+    else:
+        raise ValueError(adj_type)
+    mat = mat.tocsr().astype(np.float64)
+    mat.sort_indices()
+    rowsum = np.asarray(mat.sum(1)).ravel()
+    with np.errstate(divide="ignore"):
+        r_inv = np.power(rowsum, -1.0)
+    r_inv[np.isinf(r_inv)] = 0.0
+    coo = sparse.diags(r_inv).dot(mat).tocoo()
+    order = np.lexsort((coo.col, coo.row))
+    return coo.row[order].astype(np.int64), coo.col[order].astype(np.int64), coo.data[order].astype(np.float32)
+
+
 def isnan(x: float) -> bool:
     return math.isnan(x)

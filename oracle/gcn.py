@@ -96,6 +96,13 @@ def coo_adjacency(indptr, indices, dtype=torch.float32) -> torch.Tensor:
     return torch.sparse_coo_tensor(idx, val, (n, n), check_invariants=False)
 
 
+def coo_adjacency_general(adj_type: str, indptr, indices, n: int, dtype=torch.float32) -> torch.Tensor:
+    """The `process_graph(adj_type, ...)` tensor for any adj_type (see oracle.adjacency.process_graph_general)."""
+    r, c, v = _adj.process_graph_general(adj_type, indptr, indices, n)
+    idx = torch.from_numpy(np.vstack((r, c)).astype(np.int64))
+    return torch.sparse_coo_tensor(idx, torch.from_numpy(v).to(dtype), (n, n), check_invariants=False)
+
+
 def make_optimizer(model: nn.Module, optim: str, lr: float):
     """utils/util_methods.py:14-19."""
     if optim == "adam":

@@ -138,6 +138,48 @@ def golden_process_graph(hics, graphs):
     print("wrote process_graph.npz")
 
 
+def golden_adj_types(hics, graphs):
+    """process_graph for adj_type constant / both / none, and a ChromeGCN step on the 'both' graph."""
+    from models.ChromeModels import ChromeGCN
+    from utils import util_methods as ref_um
+    from oracle import adjacency as oadj
+    from oracle import gcn as ogcn
+    h = hics[1]
+    csr = graphs[h.chrom]
+    n = csr.shape[0]
+    pack = {"indptr": csr.indptr.astype(np.int32), "indices": csr.indices.astype(np.int32), "n": np.int64(n)}
+    for t in ("constant", "both", "none"):
+        ten = ref_um.process_graph(t, graphs, n, h.chrom).coalesce()
+        idx, val = ten.indices().numpy(), ten.values().numpy()
+        r, c, v = oadj.process_graph_general(t, csr.indptr, csr.indices, n)
+        assert np.array_equal(r, idx[0]) and np.array_equal(c, idx[1]) and np.array_equal(v, val), t
+        pack.update({t + "_rows": idx[0], t + "_cols": idx[1], t + "_vals": val})
+    d, nclass = 128, 29
+    g = torch.Generator().manual_seed(41)
+    x_f, x_r = torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+    tgt = (torch.rand(n, nclass, generator=g) < 0.1).float()
+    torch.manual_seed(6)
+    model = ogcn.stress_init_(ChromeGCN(d, d, nclass, 0.0, True, 2), seed=11)
+    pack.update(state_to_np(model.state_dict(), "sd0."))
+    pack.update({"x_f": x_f.numpy(), "x_r": x_r.numpy(), "target": tgt.numpy()})
+    adj = ref_um.process_graph("both", graphs, n, h.chrom)
+    for dt_name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        m = ChromeGCN(d, d, nclass, 0.0, True, 2)
+        m.load_state_dict(model.state_dict())
+        m = m.to(dt).train()
+        _, pf, _, _ = m(x_f.to(dt), adj.to(dt), None)
+        _, pr, _, _ = m(x_r.to(dt), adj.to(dt), None)
+        pred = (pf + pr) / 2
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, tgt.to(dt))
+        loss.backward()
+        pack["%s.pred" % dt_name] = pred.detach().numpy()
+        pack["%s.loss" % dt_name] = np.array(loss.item())
+        for k, p in m.named_parameters():
+            pack["%s.grad.%s" % (dt_name, k)] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "adj_types.npz"), **pack)
+    print("wrote adj_types.npz")
+
+
 def state_to_np(sd, prefix):
     return {prefix + k: v.detach().cpu().numpy() for k, v in sd.items()}
 
@@ -280,6 +322,7 @@ def main():
     torch.set_num_threads(1)         # deterministic reduction order for the fp32 vectors
     hics, graphs = golden_adjacency()
     golden_process_graph(hics, graphs)
+    golden_adj_types(hics, graphs)
     golden_model(hics, graphs)
     golden_finetune(hics, graphs)
 

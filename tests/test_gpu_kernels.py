@@ -268,14 +268,61 @@ def test_process_graph_golden():
 
 
 def test_process_graph_other_adj_types():
+    """adj_type constant / none (pattern kernels) and both (weighted kernels) against the reference's tensors."""
+    from scipy import sparse
     from chromegcn_b200.graph import process_graph
     from chromegcn_b200 import ops
-    n = 50
-    g = process_graph("constant", None, n, "chrZ")
-    deg = g.degrees().cpu().numpy()
-    assert deg[0] == 8 and deg[25] == 15 and deg[-1] == 8
-    gi = process_graph("none", None, n, "chrZ")
-    x = torch.randn(n, 128, device=_dev())
-    assert torch.equal(ops.spmm(gi, x), x)
-    with pytest.raises(NotImplementedError):
-        process_graph("both", {}, n, "chrZ")
+    z = np.load(os.path.join(GOLDEN, "adj_types.npz"))
+    n = int(z["n"])
+    csr = sparse.csr_matrix((np.ones(z["indices"].shape[0]), z["indices"], z["indptr"]), shape=(n, n))
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(n, 256, generator=gen)
+    for t in ("constant", "both", "none"):
+        g = process_graph(t, {"chrZ": csr}, n, "chrZ")
+        coo = g.to_sparse_coo().coalesce()
+        assert np.array_equal(coo.indices()[0].cpu().numpy(), z[t + "_rows"])
+        assert np.array_equal(coo.indices()[1].cpu().numpy(), z[t + "_cols"])
+        assert np.allclose(coo.values().cpu().numpy(), z[t + "_vals"], rtol=2e-7, atol=0)
+        assert (g.vals is not None) == (t == "both")
+        ref = torch.sparse_coo_tensor(torch.from_numpy(np.vstack((z[t + "_rows"], z[t + "_cols"]))),
+                                      torch.from_numpy(z[t + "_vals"]).double(), (n, n))
+        want = torch.sparse.mm(ref, x.double())
+        assert ogcn.max_rel(ops.spmm(g, x.to(_dev()), mean=True).cpu(), want) <= 2e-6
+        # backward operator: A_hat^T G = A (row_inv .* G)
+        t_in = x.double() * (torch.from_numpy(np.bincount(z[t + "_rows"], minlength=n)).double() * 0 + 1)   # identity scale
+        wantT = torch.sparse.mm(ref.t(), x.double())
+        if g.vals is None:
+            scaled = x / g.degrees().cpu().float()[:, None]
+        else:
+            scaled = x * g.row_inv.cpu()[:, None]
+        assert ogcn.max_rel(ops.spmm(g, scaled.to(_dev()), mean=False).cpu(), wantT) <= 2e-6
+
+
+def test_model_on_weighted_graph_matches_reference():
+    """ChromeGCN step with adj_type 'both' (weighted SpMM, row_inv row scaling in the backward GEMM)."""
+    from scipy import sparse
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.engine import ChromosomeEngine
+    from chromegcn_b200.graph import process_graph
+    z = np.load(os.path.join(GOLDEN, "adj_types.npz"))
+    n = int(z["n"])
+    csr = sparse.csr_matrix((np.ones(z["indices"].shape[0]), z["indices"], z["indptr"]), shape=(n, n))
+    g = process_graph("both", {"c": csr}, n, "c")
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0.")}
+    nclass = sd["out.weight"].shape[0]
+    for impl in (1, 0):
+        m = ChromeGCN(128, 128, nclass, 0.0, True, 2)
+        m.load_state_dict(sd)
+        m = m.to(_dev()).train()
+        m.gemm_impl = impl
+        eng = ChromosomeEngine(m, 2)
+        loss = torch.zeros(1, device=_dev())
+        xg = torch.empty(n, 2, 128, device=_dev())
+        out, _ = eng.run(g, eng.pack(torch.from_numpy(z["x_f"]).to(_dev()), torch.from_numpy(z["x_r"]).to(_dev())),
+                         torch.from_numpy(z["target"]).to(_dev()), None, loss, train=True, input_grad=xg)
+        assert ogcn.max_rel(out.mean(1).cpu(), torch.from_numpy(z["f32.pred"])) <= 1e-5
+        assert abs(loss.item() - float(z["f32.loss"])) <= 1e-5 * abs(float(z["f32.loss"]))
+        for k, p in m.named_parameters():
+            ref64 = torch.from_numpy(z["f64.grad." + k])
+            own = ogcn.max_rel(torch.from_numpy(z["f32.grad." + k]), ref64)
+            assert ogcn.max_rel(p.grad.cpu(), ref64) <= max(1e-5, 3 * own), (impl, k)

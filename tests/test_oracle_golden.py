@@ -114,3 +114,15 @@ def test_finetune_matches_reference(golden_dir):
         assert ogcn.max_rel(pv, torch.from_numpy(z["epoch%d.valid_preds" % epoch])) <= 1e-5
     for k, v in m.state_dict().items():
         assert ogcn.max_rel(v.float(), torch.from_numpy(z["sd3." + k]).float()) <= 2e-5, k
+
+
+def test_process_graph_all_adj_types(golden_dir):
+    """utils/util_methods.py:146-180 for adj_type constant / both / none (coalesced COO of the reference)."""
+    z = np.load(os.path.join(golden_dir, "adj_types.npz"))
+    n = int(z["n"])
+    for t in ("constant", "both", "none"):
+        r, c, v = oadj.process_graph_general(t, z["indptr"], z["indices"], n)
+        assert np.array_equal(r, z[t + "_rows"]) and np.array_equal(c, z[t + "_cols"]) and np.array_equal(v, z[t + "_vals"])
+    # 'both' is genuinely weighted: values differ inside a row
+    r, c, v = oadj.process_graph_general("both", z["indptr"], z["indices"], n)
+    assert any(len(set(v[r == i].tolist())) > 1 for i in range(n))
