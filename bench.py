@@ -339,8 +339,9 @@ def main():
                            "gate": True, "adj_type": "hic", "hicnorm": "SQRTVC", "hicsize": HIC_EDGES, "optim": "sgd",
                            "gcn_dropout": DROPOUT, "strands": 2, "total_stored_entries": total_edges,
                            "parallelism": "chromosome-sharded x%d (LPT), flat-gradient allreduce per round" % world,
-                           "l2": "inputs larger than L2: each step streams ~%.1f GB of panels" % (
-                               total_edges and sum(sizes[c] for c in chroms) * 2 * D * 4 * 20 / 1e9),
+                           "l2": "inputs larger than L2 (126 MB): %.2f GB of resident feature panels + targets cycled per "
+                                 "step, ~50 panel-sized passes per chromosome" % (
+                                     sum(sizes[c] for c in chroms) * (2 * D * 4 + NCLASS * 4) / 1e9),
                            "gemm_impl": args.gemm_impl, "final_loss_sum": final_loss},
                 "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}

@@ -145,8 +145,9 @@ class HiCGraph:
                                                _lib.current_stream()), "cgcn_coo_to_pattern")
         if not flags.value & 1:
             raise NotImplementedError(
-                "adjacency values are not 1/deg(row): only mean-aggregation graphs (adj_type hic / constant / none) "
-                "run on the pattern-only kernels; adj_type 'both' and arbitrary weights are not implemented yet")
+                "adjacency values are not 1/deg(row): a normalised weighted tensor does not reveal the raw symmetric "
+                "weights the backward pass needs; build the graph with process_graph('both', ...) or "
+                "graph.weighted_from_scipy(A_raw) instead")
         if not flags.value & 2:
             raise NotImplementedError("adjacency pattern is not symmetric; the backward SpMM relies on P = P^T")
         return cls(rp, ci, n, nnz, name)
