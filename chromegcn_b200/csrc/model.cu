@@ -105,12 +105,37 @@ int gemm_gram_dispatch(const float* A, int64_t lda, const float* B, int64_t ldb,
   return gemm_gram_ffma(A, lda, B, ldb, C, ldc, m, ka, nb, accumulate, ws, ws_bytes, stream);
 }
 
+// ---- side stream: weight-gradient contractions and gradient finalizes are off the critical path of the
+// backward pass (nothing downstream reads them before the optimiser step), so they run on a helper stream
+// forked from / joined to the caller's stream with events.  One helper per host thread and device, created on
+// first use (the only resources this library ever creates).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t join = nullptr;
+};
+static int side_stream(SideStream** out) {
+  static thread_local SideStream table[64];
+  int dev = 0;
+  CGCN_CUDA(cudaGetDevice(&dev));
+  CGCN_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  SideStream& s = table[dev];
+  if (s.stream == nullptr) {
+    CGCN_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) CGCN_CUDA(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
+    CGCN_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return CGCN_OK;
+}
+
 // ---- workspace layout (offsets in floats)
 struct WsLayout {
   size_t ax[2], z[2], xo[2], hb;
   size_t bn_mean, bn_rstd, bn_c1, bn_c2;
-  size_t dA, dB, dC;
-  size_t partial, partial_floats;
+  size_t dA, dB, dC, dD;
+  size_t partial, partial_floats;      // main-stream reductions (BatchNorm)
+  size_t partial_l[2], partial_side;   // per-layer gate-backward partials and the side stream's own (column sums)
   size_t gram, gram_bytes;
   size_t tc, tc_bytes;
   size_t total_floats;
@@ -141,11 +166,15 @@ static WsLayout make_layout(int n, int d, int nclass, int layers, int strands) {
   L.dA = take(panel);
   L.dB = take(panel);
   L.dC = take(panel);
+  L.dD = take(panel);
   size_t per = static_cast<size_t>(2) * strands * d;
   if (per < static_cast<size_t>(2 * d + 4)) per = 2 * d + 4;
   if (per < 128) per = 128;
   L.partial_floats = static_cast<size_t>(rowwise_max_grid()) * per;
   L.partial = take(L.partial_floats);
+  L.partial_l[0] = take(L.partial_floats);
+  L.partial_l[1] = take(L.partial_floats);
+  L.partial_side = take(L.partial_floats);
   L.gram_bytes = gram_workspace_bytes(static_cast<int64_t>(n) * strands);
   L.gram = take((L.gram_bytes + 3) / 4);
   L.tc_bytes = tc_workspace_bytes();
@@ -191,7 +220,8 @@ static int validate(const cgcn_model* m, bool backward) {
 int gate_fwd_launch(const GateFwdArgs& a, int d, int S, bool stats, int* grid_out, cudaStream_t stream);
 int bn_apply_launch(const BnApplyArgs& a, cudaStream_t stream);
 int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, cudaStream_t stream);
-int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, float* db, float* dwg, float* dbg, cudaStream_t stream);
+int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, int* grid_out, cudaStream_t stream);
+int gate_bwd_finalize_launch(const float* partial, int grid, int d, float* db, float* dwg, float* dbg, cudaStream_t stream);
 
 static int model_forward(const cgcn_model* m) {
   tls_rp_ordinal = tls_gr_ordinal = 0;
@@ -255,6 +285,11 @@ static int model_forward(const cgcn_model* m) {
 static int model_backward(const cgcn_model* m) {
   CGCN_TRY(validate(m, true));
   cudaStream_t st = static_cast<cudaStream_t>(m->stream);
+  SideStream* side = nullptr;
+  CGCN_TRY(side_stream(&side));
+  cudaStream_t ss = side->stream;
+  static const bool serial = getenv("CGCN_NO_SIDE_STREAM") != nullptr;   // developer aid: everything on the caller's stream
+  if (serial) ss = st;
   const int n = m->graph.n, d = m->d, S = m->strands, C = m->nclass, L = m->layers;
   const int W = S * d;
   const int64_t M = static_cast<int64_t>(n) * S;
@@ -264,16 +299,26 @@ static int model_backward(const cgcn_model* m) {
   float* dA = ws + lay.dA;
   float* dB = ws + lay.dB;
   float* dC = ws + lay.dC;
-  void* gram_ws = ws + lay.gram;
+  float* dD = ws + lay.dD;
+  void* gram_ws = ws + lay.gram;               // used by the side stream only
+  int fork_id = 0;
+  auto fork = [&]() -> int {                    // side stream waits for everything enqueued on `st` so far
+    if (serial) return CGCN_OK;
+    CGCN_CUDA(cudaEventRecord(side->fork[fork_id], st));
+    CGCN_CUDA(cudaStreamWaitEvent(ss, side->fork[fork_id], 0));
+    fork_id = (fork_id + 1) & 3;
+    return CGCN_OK;
+  };
 
-  // head: d out.weight = dout^T hb ; d out.bias = colsum(dout) ; d hb = dout Wout
+  // head.  side: d out.weight = dout^T hb ; d out.bias = colsum(dout).   main: d hb = dout Wout
   const int ldo = m->out_ld > 0 ? m->out_ld : C;
+  CGCN_TRY(fork());
   CGCN_TRY(gemm_gram_dispatch(m->out_grad, ldo, ws + lay.hb, d, m->grads.out_w, d, M, C, d, 0, m->gemm_impl, gram_ws,
-                              lay.gram_bytes, st));
-  CGCN_TRY(colsum_launch(m->out_grad, M, C, ldo, m->grads.out_b, ws + lay.partial, st));
+                              lay.gram_bytes, ss));
+  CGCN_TRY(colsum_launch(m->out_grad, M, C, ldo, m->grads.out_b, ws + lay.partial_side, ss));
   CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, ldo, m->params.out_w, 0, nullptr, dA, d, M, d, C, nullptr, nullptr, 1, m->gemm_impl,
                                   tcws, lay.tc_bytes, st));
-  // BatchNorm backward sums
+  // BatchNorm backward sums (needed by the next kernel: stays on the main stream)
   {
     BnBwdReduceArgs r{};
     r.dhb = dA;
@@ -288,15 +333,17 @@ static int model_backward(const cgcn_model* m) {
     CGCN_TRY(bn_bwd_finalize_launch(ws + lay.partial, grid, n, S, d, m->training, ws + lay.bn_c1, ws + lay.bn_c2,
                                     m->grads.bn_w, m->grads.bn_b, st));
   }
-  // layers, last to first.  `src` holds the gradient entering the layer's gate stage.
+  // layers, last to first.  Four scratch panels: `src` (gradient entering the gate stage), dy, dxd, and the
+  // SpMM output; dy stays untouched by the main stream while the side stream's gram kernel reads it.
+  //   layer L-1: src = dA, dy = dB, dxd = dC, t -> dA, dx -> dD
+  //   layer L-2: src = dD, dy = dA, dxd = dC, t -> dD, dx -> x_in_grad
   const float* src = dA;
   for (int l = L - 1; l >= 0; --l) {
     const bool head = (l == L - 1);
     const bool need_dx = (l > 0) || m->need_input_grad;
     const float* xin = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
-    // the three scratch panels rotate: src is one of them, dy and dxd take the other two
     float* dy = (src == dA) ? dB : dA;
-    float* dxd = (src == dC) ? ((dy == dA) ? dB : dA) : dC;
+    float* dxd = dC;
     GateBwdArgs a{};
     a.dsrc = src;
     a.h = ws + lay.xo[l];
@@ -311,22 +358,30 @@ static int model_backward(const cgcn_model* m) {
     a.wg = m->params.gate_w[l];
     a.dy = dy;
     a.dxd = need_dx ? dxd : nullptr;
-    a.partial = ws + lay.partial;
+    a.partial = ws + lay.partial_l[l];
     a.n = n;
     a.drop = head ? make_dropout(m->dropout_p, m->seed, m->step, 1, m->training)
                   : make_dropout(m->dropout_p, m->seed, m->step, 0, m->training);
-    CGCN_TRY(gate_bwd_launch(a, d, S, head, m->grads.gc_b[l], m->grads.gate_w[l], m->grads.gate_b[l], st));
-    // d W = (A_hat x)^T dy
+    int grid = 0;
+    CGCN_TRY(gate_bwd_launch(a, d, S, head, &grid, st));
+    // side: bias / gate gradients from the partials, d W = (A_hat x)^T dy
+    CGCN_TRY(fork());
+    CGCN_TRY(gate_bwd_finalize_launch(ws + lay.partial_l[l], grid, d, m->grads.gc_b[l], m->grads.gate_w[l],
+                                      m->grads.gate_b[l], ss));
     CGCN_TRY(gemm_gram_dispatch(ws + lay.ax[l], d, dy, d, m->grads.gc_w[l], d, M, d, d, 0, m->gemm_impl, gram_ws,
-                                lay.gram_bytes, st));
+                                lay.gram_bytes, ss));
     if (!need_dx) break;
-    // t = D^-1 (dy W^T)  ->  the panel that held `src` ; then dx = dxd + P t
+    // main: t = D^-1 (dy W^T) -> the panel that held `src` ; then dx = dxd + P t
     float* t = const_cast<float*>(src);
     CGCN_TRY(gemm_rowpanel_dispatch(dy, d, m->params.gc_w[l], 1, nullptr, t, d, M, d, d, m->graph.rowptr, m->graph.row_inv, S, m->gemm_impl,
                                     tcws, lay.tc_bytes, st));
-    float* dx = (l == 0) ? m->x_in_grad : dy;          // dy is dead after the two contractions above
+    float* dx = (l == 0) ? m->x_in_grad : dD;
     CGCN_TRY(spmm_launch(&m->graph, t, dx, W, 0, dxd, st));
     src = dx;
+  }
+  if (!serial) {                                // join: the caller's stream owns every gradient again
+    CGCN_CUDA(cudaEventRecord(side->join, ss));
+    CGCN_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   }
   return CGCN_OK;
 }

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 // ------------------------------------------------------------------------------ BN backward sums
 
 template <int DV, int S>
-__global__ void __launch_bounds__(RW_THREADS) bn_bwd_reduce_kernel(const BnBwdReduceArgs a) {
+__global__ void __launch_bounds__(RW_THREADS, (DV == 1) ? 4 : 1) bn_bwd_reduce_kernel(const BnBwdReduceArgs a) {
   constexpr int D = DV * 128;
   constexpr int K = 2 * S * D;
   extern __shared__ __align__(16) float red[];
@@ -464,8 +464,10 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
         continue;
       }
       const float pm = p[u] * inv_s;                            // (pred_f + pred_r) / 2, finetune.py:43
-      local += fmaxf(pm, 0.f) - pm * t[u] + log1pf(expf(-fabsf(pm)));   // BCE-with-logits, finetune.py:45
-      const float pr = sigmoidf_(pm);
+      const float en = expf(-fabsf(pm));                        // one exponential serves the loss and the sigmoid
+      local += fmaxf(pm, 0.f) - pm * t[u] + log1pf(en);         // BCE-with-logits, finetune.py:45
+      const float rinv = 1.0f / (1.0f + en);
+      const float pr = pm >= 0.f ? rinv : en * rinv;
       if (a.probs != nullptr) a.probs[rr[u] * C + cc[u]] = pr;  // F.sigmoid(pred), finetune.py:52
       if (a.out_grad != nullptr) {
         const float gsc = (pr - t[u]) * a.inv_count * inv_s;
@@ -638,9 +640,11 @@ int bn_bwd_finalize_launch(const float* partial, int parts, int n, int S, int D,
   return check_launch("bn_bwd_finalize_kernel");
 }
 
-int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, float* db, float* dwg, float* dbg,
-                    cudaStream_t stream) {
+// The kernel only; its per-CTA partials are reduced by gate_bwd_finalize_launch (possibly on another stream:
+// the bias / gate gradients are not on the critical path of the backward pass).
+int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, int* grid_out, cudaStream_t stream) {
   const int grid = rowwise_grid(a.n);
+  if (grid_out) *grid_out = grid;
   const int dv = d / 128;
   const int K = 2 * d + 4;
   const size_t smem = static_cast<size_t>(RW_WARPS) * K * sizeof(float);
@@ -654,9 +658,14 @@ int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, float* db, fl
   }
   DISPATCH_DV_S(dv, S, GBW);
 #undef GBW
-  CGCN_TRY(check_launch("gate_bwd_kernel"));
+  return check_launch("gate_bwd_kernel");
+}
+
+int gate_bwd_finalize_launch(const float* partial, int grid, int d, float* db, float* dwg, float* dbg,
+                             cudaStream_t stream) {
+  const int K = 2 * d + 4;
   ColFinalizeArgs f{};
-  f.partial = a.partial;
+  f.partial = partial;
   f.parts = grid;
   f.stride = K;
   f.dst[0] = db;  f.begin[0] = 0;      f.len[0] = d;

@@ -15,7 +15,9 @@
  *     output size is data dependent (they synchronise `stream` before returning);
  *   - return value: 0 = ok, negative = error (cgcn_status); cgcn_last_error() returns a
  *     thread-local message for the last failing call of the calling thread;
- *   - thread-safe for distinct streams / buffers; no global mutable state but that string;
+ *   - thread-safe for distinct streams / buffers; no global mutable state but that string and, per host
+ *     thread and device, one helper stream + events created on the first cgcn_model_backward (weight-gradient
+ *     contractions run there, forked from and joined back to the caller's stream with events);
  *   - there is NO CPU fallback: on a machine without an sm_100 device every compute call
  *     returns CGCN_ERR_CUDA.
  *
