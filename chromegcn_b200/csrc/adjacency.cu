@@ -4,8 +4,8 @@
 // pattern conversion for callers that still hold the reference's torch sparse tensor.
 //
 // All of it is integer / fp64 compare work bound by HBM traffic of the sort passes.  The
-// device-wide primitives (LSD radix sort, prefix sum) are cub:: (header-only, part of the CUDA
-// toolkit, compiled into this library); the contract-specific stages are the kernels below:
+// device-wide primitives (stable LSD radix sort, prefix sum) are hand-written too (radix_sort.cuh);
+// the contract-specific stages are the kernels below:
 //   filter      binary-search both bins in the sorted window starts, fp64 normalise,
 //               accept flag                                                    (:78-86)
 //   dedup       stable sort by (i,j) key with the accepted-order index as payload; per key
@@ -14,10 +14,10 @@
 //               of -value  => "sorted(items, key=value, reverse=True)" with ties in insertion
 //               order (:94); first K
 //   symmetrise  (i,j),(j,i) keys, sort, unique, rowptr by binary search          (:108-120)
-#include <cub/cub.cuh>
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace cgcn {
 
@@ -176,21 +176,17 @@ static int bits_for(int64_t count) {          // bits needed to represent values
   return b;
 }
 
-static size_t cub_temp_bytes(int64_t items) {
+static size_t cub_temp_bytes(int64_t items) {      // scratch of the sort / scan primitives for `items` elements
   if (items < 1) items = 1;
-  const int cnt = static_cast<int>(items);
-  size_t best = 0, t = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, t, static_cast<u64*>(nullptr), static_cast<u64*>(nullptr),
-                                  static_cast<u32*>(nullptr), static_cast<u32*>(nullptr), cnt);
-  best = t > best ? t : best;
-  cub::DeviceRadixSort::SortPairs(nullptr, t, static_cast<u32*>(nullptr), static_cast<u32*>(nullptr),
-                                  static_cast<u32*>(nullptr), static_cast<u32*>(nullptr), cnt);
-  best = t > best ? t : best;
-  cub::DeviceRadixSort::SortKeys(nullptr, t, static_cast<u64*>(nullptr), static_cast<u64*>(nullptr), cnt);
-  best = t > best ? t : best;
-  cub::DeviceScan::InclusiveSum(nullptr, t, static_cast<int*>(nullptr), static_cast<int*>(nullptr), cnt);
-  best = t > best ? t : best;
-  return best + 256;
+  const size_t a = rsort::sort_temp_bytes(items), b = rsort::scan_temp_bytes(items);
+  return (a > b ? a : b) + 256;
+}
+
+template <typename T>
+static void swap_ptr(T*& a, T*& b) {
+  T* t = a;
+  a = b;
+  b = t;
 }
 
 struct AdjWs {
@@ -262,13 +258,13 @@ extern "C" int cgcn_adj_build(const int64_t* bin1, const int64_t* bin2, const do
     CGCN_CUDA(cudaStreamSynchronize(st));
     return CGCN_OK;
   }
-  size_t tb = w.cub_bytes;
+  bool in_b = false;
 
   // 1. filter + normalise
   adj_filter_kernel<<<blocks_for(m), 256, 0, st>>>(bin1, bin2, val, m, window_starts, n, norm, norm_len, res_bp, use_norm,
                                                    w.key, w.v, w.flag, w.err_count);
   CGCN_TRY(check_launch("adj_filter_kernel"));
-  CGCN_CUDA(cub::DeviceScan::InclusiveSum(w.cub_temp, tb, w.flag, w.incl, static_cast<int>(m), st));
+  CGCN_TRY((rsort::prefix_sum<int, true>(w.flag, w.incl, m, w.cub_temp, st)));
   const int64_t limit = (!use_norm && k_pairs > 0) ? k_pairs : -1;
   adj_compact_kernel<<<blocks_for(m), 256, 0, st>>>(w.key, w.v, w.flag, w.incl, m, limit, w.key_c, w.v_c, w.idx_c,
                                                     w.err_count);
@@ -295,13 +291,14 @@ extern "C" int cgcn_adj_build(const int64_t* bin1, const int64_t* bin2, const do
 
   // 2. dict semantics: group by key
   const int key_bits = 32 + bits_for(n);
-  tb = w.cub_bytes;
-  CGCN_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.key_c, w.key_s, w.idx_c, w.idx_s, static_cast<int>(ma), 0,
-                                            key_bits, st));
+  CGCN_TRY(rsort::radix_sort<u64>(w.key_c, w.key_s, w.idx_c, w.idx_s, ma, 0, key_bits, w.cub_temp, st, &in_b));
+  if (!in_b) {                                   // sorted data sits in the (key_c, idx_c) pair: make *_s the sorted one
+    swap_ptr(w.key_c, w.key_s);
+    swap_ptr(w.idx_c, w.idx_s);
+  }
   adj_heads_kernel<<<blocks_for(ma), 256, 0, st>>>(w.key_s, ma, w.head);
   CGCN_TRY(check_launch("adj_heads_kernel"));
-  tb = w.cub_bytes;
-  CGCN_CUDA(cub::DeviceScan::InclusiveSum(w.cub_temp, tb, w.head, w.incl, static_cast<int>(ma), st));
+  CGCN_TRY((rsort::prefix_sum<int, true>(w.head, w.incl, ma, w.cub_temp, st)));
   adj_groups_kernel<<<blocks_for(ma), 256, 0, st>>>(w.key_s, w.idx_s, w.head, w.incl, w.v_c, ma, w.ukey, w.upos, w.uvkey,
                                                     w.iota);
   CGCN_TRY(check_launch("adj_groups_kernel"));
@@ -311,24 +308,28 @@ extern "C" int cgcn_adj_build(const int64_t* bin1, const int64_t* bin2, const do
   const int64_t u = u_host;
 
   // 3. stable descending rank: by insertion position, then by value key
-  tb = w.cub_bytes;
-  CGCN_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.upos, w.upos_s, w.iota, w.perm1, static_cast<int>(u), 0,
-                                            bits_for(ma), st));
+  CGCN_TRY(rsort::radix_sort<u32>(w.upos, w.upos_s, w.iota, w.perm1, u, 0, bits_for(ma), w.cub_temp, st, &in_b));
+  if (!in_b) {
+    swap_ptr(w.upos, w.upos_s);
+    swap_ptr(w.iota, w.perm1);
+  }
   adj_gather_vkey_kernel<<<blocks_for(u), 256, 0, st>>>(w.uvkey, w.perm1, u, w.vk_a);
   CGCN_TRY(check_launch("adj_gather_vkey_kernel"));
-  tb = w.cub_bytes;
-  CGCN_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.vk_a, w.vk_b, w.perm1, w.perm2, static_cast<int>(u), 0, 64, st));
+  CGCN_TRY(rsort::radix_sort<u64>(w.vk_a, w.vk_b, w.perm1, w.perm2, u, 0, 64, w.cub_temp, st, &in_b));
+  if (!in_b) {
+    swap_ptr(w.vk_a, w.vk_b);
+    swap_ptr(w.perm1, w.perm2);
+  }
   const int64_t ksel = (k_pairs > 0 && k_pairs < u) ? k_pairs : u;
 
   // 4. symmetrise, unique, CSR
   adj_symmetrise_kernel<<<blocks_for(ksel), 256, 0, st>>>(w.ukey, w.perm2, ksel, w.sym);
   CGCN_TRY(check_launch("adj_symmetrise_kernel"));
-  tb = w.cub_bytes;
-  CGCN_CUDA(cub::DeviceRadixSort::SortKeys(w.cub_temp, tb, w.sym, w.sym_s, static_cast<int>(2 * ksel), 0, key_bits, st));
+  CGCN_TRY(rsort::radix_sort<u64>(w.sym, w.sym_s, nullptr, nullptr, 2 * ksel, 0, key_bits, w.cub_temp, st, &in_b));
+  if (!in_b) swap_ptr(w.sym, w.sym_s);
   adj_heads_kernel<<<blocks_for(2 * ksel), 256, 0, st>>>(w.sym_s, 2 * ksel, w.head);
   CGCN_TRY(check_launch("adj_heads_kernel"));
-  tb = w.cub_bytes;
-  CGCN_CUDA(cub::DeviceScan::InclusiveSum(w.cub_temp, tb, w.head, w.incl, static_cast<int>(2 * ksel), st));
+  CGCN_TRY((rsort::prefix_sum<int, true>(w.head, w.incl, 2 * ksel, w.cub_temp, st)));
   int nnz_h = 0;
   CGCN_CUDA(cudaMemcpyAsync(&nnz_h, w.incl + (2 * ksel - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
   CGCN_CUDA(cudaStreamSynchronize(st));
@@ -395,8 +396,7 @@ __global__ void selfloop_fill_kernel(const int32_t* __restrict__ rowptr, const i
 
 extern "C" int cgcn_adj_add_selfloops_workspace_bytes(int32_t n, size_t* bytes_host) {
   CGCN_REQUIRE(bytes_host != nullptr && n >= 0, "cgcn_adj_add_selfloops_workspace_bytes: bad argument");
-  size_t t = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, t, static_cast<int*>(nullptr), static_cast<int*>(nullptr), n < 1 ? 1 : n);
+  const size_t t = rsort::scan_temp_bytes(n < 1 ? 1 : n);
   *bytes_host = align_up(static_cast<size_t>(n < 1 ? 1 : n) * sizeof(int), 256) * 2 + t + 1024;
   return CGCN_OK;
 }
@@ -415,12 +415,10 @@ extern "C" int cgcn_adj_add_selfloops(const int32_t* rowptr, const int32_t* coli
   Arena a(workspace, workspace_bytes);
   int* cnt = a.take<int>(n);
   int* incl = a.take<int>(n);
-  size_t tb = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, tb, cnt, incl, n);
-  void* temp = a.take<char>(tb);
+  void* temp = a.take<char>(rsort::scan_temp_bytes(n));
   selfloop_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowptr, colidx, n, cnt);
   CGCN_TRY(check_launch("selfloop_count_kernel"));
-  CGCN_CUDA(cub::DeviceScan::InclusiveSum(temp, tb, cnt, incl, n, st));
+  CGCN_TRY((rsort::prefix_sum<int, true>(cnt, incl, n, temp, st)));
   selfloop_rowptr_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(incl, n, rowptr_out);
   CGCN_TRY(check_launch("selfloop_rowptr_kernel"));
   const int64_t threads = static_cast<int64_t>(n) * 32;
@@ -486,12 +484,16 @@ extern "C" int cgcn_coo_to_pattern(const int64_t* rows, const int64_t* cols, con
   u32* iota = a.take<u32>(nnz);
   u32* perm = a.take<u32>(nnz);
   int* viol = a.take<int>(4);
-  size_t tb = cub_temp_bytes(nnz);
-  void* temp = a.take<char>(tb);
+  void* temp = a.take<char>(cub_temp_bytes(nnz));
+  bool in_b = false;
   CGCN_CUDA(cudaMemsetAsync(viol, 0, 4 * sizeof(int), st));
   coo_keys_kernel<<<blocks_for(nnz), 256, 0, st>>>(rows, cols, nnz, n, key, iota, viol);
   CGCN_TRY(check_launch("coo_keys_kernel"));
-  CGCN_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, key, key_s, iota, perm, static_cast<int>(nnz), 0, 32 + bits_for(n), st));
+  CGCN_TRY(rsort::radix_sort<u64>(key, key_s, iota, perm, nnz, 0, 32 + bits_for(n), temp, st, &in_b));
+  if (!in_b) {
+    swap_ptr(key, key_s);
+    swap_ptr(iota, perm);
+  }
   adj_rowptr_kernel<<<blocks_for(n + 1), 256, 0, st>>>(key_s, nnz, n, rowptr);
   CGCN_TRY(check_launch("adj_rowptr_kernel"));
   coo_check_kernel<<<blocks_for(nnz), 256, 0, st>>>(key_s, perm, vals, nnz, rowptr, colidx, viol);

@@ -427,11 +427,13 @@ struct BceArgs {
   float inv_count;     // 1 / (n*C)
 };
 
+template <int SS>
 __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
   __shared__ float wsum[8];
   float local = 0.f;
-  const float inv_s = 1.0f / a.S;
-  const uint32_t total = static_cast<uint32_t>(a.total), C = static_cast<uint32_t>(a.C), S = static_cast<uint32_t>(a.S);
+  constexpr uint32_t S = SS;                                    // compile-time: the strand loads issue back to back
+  const float inv_s = 1.0f / S;
+  const uint32_t total = static_cast<uint32_t>(a.total), C = static_cast<uint32_t>(a.C);
   const uint32_t LD = static_cast<uint32_t>(a.ld);
   // flat over the n x ld elements (padding columns only get a zero gradient), 4 independent elements per
   // thread per trip (coalesced, 32-bit index math)
@@ -449,8 +451,12 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
         cc[u] = e - rr[u] * LD;
         ob[u] = rr[u] * S * LD + cc[u];                         // (r*S + 0)*ld + c
         if (cc[u] < C) {
-          for (uint32_t s = 0; s < S; ++s) p[u] += __ldg(a.out + ob[u] + s * LD);
+          float ps[SS];
+#pragma unroll
+          for (uint32_t s = 0; s < S; ++s) ps[s] = __ldg(a.out + ob[u] + s * LD);
           t[u] = __ldg(a.target + rr[u] * C + cc[u]);
+#pragma unroll
+          for (uint32_t s = 0; s < S; ++s) p[u] += ps[s];
         }
       }
     }
@@ -459,8 +465,10 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
       const uint32_t e = e0 + u * 256u;
       if (e >= total) continue;
       if (cc[u] >= C) {
-        if (a.out_grad != nullptr)
+        if (a.out_grad != nullptr) {
+#pragma unroll
           for (uint32_t s = 0; s < S; ++s) a.out_grad[ob[u] + s * LD] = 0.f;
+        }
         continue;
       }
       const float pm = p[u] * inv_s;                            // (pred_f + pred_r) / 2, finetune.py:43
@@ -471,6 +479,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
       if (a.probs != nullptr) a.probs[rr[u] * C + cc[u]] = pr;  // F.sigmoid(pred), finetune.py:52
       if (a.out_grad != nullptr) {
         const float gsc = (pr - t[u]) * a.inv_count * inv_s;
+#pragma unroll
         for (uint32_t s = 0; s < S; ++s) a.out_grad[ob[u] + s * LD] = gsc;
       }
     }
@@ -707,7 +716,8 @@ int bce_launch(const float* out, const float* target, int n, int C, int S, int l
   int grid = static_cast<int>((a.total + 1023) / 1024);
   if (grid > bce_grid()) grid = bce_grid();
   if (grid < 1) grid = 1;
-  bce_kernel<<<grid, 256, 0, stream>>>(a);
+  if (S == 1) bce_kernel<1><<<grid, 256, 0, stream>>>(a);
+  else bce_kernel<2><<<grid, 256, 0, stream>>>(a);
   CGCN_TRY(check_launch("bce_kernel"));
   bce_finalize_kernel<<<1, 256, 0, stream>>>(partial, grid, a.inv_count, loss_sum);
   return check_launch("bce_finalize_kernel");
