@@ -11,7 +11,7 @@ from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libchromegcn.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ChromeGCNNativeError(RuntimeError):
@@ -34,13 +34,14 @@ class Model(C.Structure):
                 ("d", C.c_int32), ("nclass", C.c_int32), ("layers", C.c_int32), ("strands", C.c_int32),
                 ("training", C.c_int32), ("gemm_impl", C.c_int32), ("need_input_grad", C.c_int32),
                 ("out_ld", C.c_int32),
-                ("dropout_p", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("reserved1", C.c_float),
+                ("dropout_p", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("row_begin", C.c_int32),
                 ("seed", C.c_uint64), ("step", C.c_uint64),
                 ("params", Params), ("grads", Params),
                 ("bn_running_mean", C.c_void_p), ("bn_running_var", C.c_void_p), ("bn_num_batches_tracked", C.c_void_p),
                 ("x_in", C.c_void_p), ("x_in_grad", C.c_void_p), ("out", C.c_void_p), ("gate", C.c_void_p * 2),
                 ("out_grad", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p),
+                ("n_total", C.c_int64), ("x_full", C.c_void_p), ("bn_sums", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -68,7 +69,8 @@ PROTOTYPES = {
     "cgcn_model_forward": (C.c_int, [C.POINTER(Model)]),
     "cgcn_model_backward": (C.c_int, [C.POINTER(Model)]),
     "cgcn_bce_workspace_bytes": (_SZ, [_I32, _I32]),
-    "cgcn_bce_loss": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "cgcn_bce_loss": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "cgcn_model_phase": (C.c_int, [C.POINTER(Model), _I32, _I32, C.POINTER(_P)]),
     "cgcn_train_step": (C.c_int, [C.POINTER(Model), _P, _P, _P, _P]),
     "cgcn_sgd_step": (C.c_int, [_P, _P, _P, _I64, _F32, _F32, _F32, _F32, _P]),
     "cgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _I64, _F32, _P]),

@@ -109,10 +109,13 @@ struct DropoutCfg {
   uint2 key;            // seed
   uint32_t step_lo, step_hi_site;   // counter words 2,3
   int enabled;
+  unsigned long long elem4_offset;  // added to the local float4 index: global position of a row-partitioned panel
 };
 
-inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t step, int site, bool training) {
+inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t step, int site, bool training,
+                               unsigned long long elem4_offset = 0) {
   DropoutCfg c;
+  c.elem4_offset = elem4_offset;
   c.enabled = (training && p > 0.0f) ? 1 : 0;
   double t = static_cast<double>(p) * 4294967296.0;
   if (t > 4294967295.0) t = 4294967295.0;
@@ -127,6 +130,7 @@ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t step, int site, 
 
 // keep-mask multipliers for the 4 consecutive floats starting at flat element index `elem4 * 4`
 __device__ __forceinline__ float4 dropout_mult4(const DropoutCfg& c, uint64_t elem4) {
+  elem4 += c.elem4_offset;
   const uint4 r = philox4x32_10(
       make_uint4(static_cast<uint32_t>(elem4), static_cast<uint32_t>(elem4 >> 32), c.step_lo, c.step_hi_site), c.key);
   float4 m;

@@ -36,13 +36,13 @@ size_t tc_workspace_bytes();
 int rowwise_max_grid();
 int bce_grid();
 int bce_launch(const float* out, const float* target, int n, int C, int S, int ld, float* probs, float* loss_sum,
-               float* out_grad, float* partial, cudaStream_t stream);
+               float* out_grad, float* partial, int64_t n_total, cudaStream_t stream);
 int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* dst, float* partial, cudaStream_t stream);
-int bn_finalize_launch(const float* partial, int parts, int n, int S, int D, float eps, float momentum, int training,
+int bn_finalize_launch(const float* partial, int parts, int64_t n, int S, int D, float eps, float momentum, int training,
                        float* running_mean, float* running_var, int64_t* nbt, float* mean_out, float* rstd_out,
-                       cudaStream_t stream);
-int bn_bwd_finalize_launch(const float* partial, int parts, int n, int S, int D, int training, float* c1, float* c2,
-                           float* dgamma, float* dbeta, cudaStream_t stream);
+                       const double* presummed, double* sums_out, cudaStream_t stream);
+int bn_bwd_finalize_launch(const float* partial, int parts, int64_t n, int S, int D, int training, float* c1, float* c2,
+                           float* dgamma, float* dbeta, const double* presummed, double* sums_out, cudaStream_t stream);
 
 // ---- error string / counters
 static thread_local char tls_error[512] = "";
@@ -199,7 +199,8 @@ static int validate(const cgcn_model* m, bool backward) {
     CGCN_REQUIRE(m->params.gc_w[l] && m->params.gc_b[l] && m->params.gate_w[l] && m->params.gate_b[l],
                  "cgcn_model: null layer-%d parameter", l);
   CGCN_REQUIRE(m->params.bn_w && m->params.bn_b && m->params.out_w && m->params.out_b, "cgcn_model: null head parameter");
-  CGCN_REQUIRE(!(m->training && m->graph.n < 2), "cgcn_model: BatchNorm1d in training mode needs more than 1 row");
+  CGCN_REQUIRE(!(m->training && (m->n_total > 0 ? m->n_total : m->graph.n) < 2),
+               "cgcn_model: BatchNorm1d in training mode needs more than 1 row");
   const size_t need = cgcn_model_workspace_bytes(m->graph.n, m->d, m->nclass, m->layers, m->strands);
   if (m->workspace == nullptr || m->workspace_bytes < need) {
     set_error("cgcn_model: workspace %zu < %zu bytes", m->workspace_bytes, need);
@@ -223,167 +224,289 @@ int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, 
 int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, int* grid_out, cudaStream_t stream);
 int gate_bwd_finalize_launch(const float* partial, int grid, int d, float* db, float* dwg, float* dbg, cudaStream_t stream);
 
-static int model_forward(const cgcn_model* m) {
-  tls_rp_ordinal = tls_gr_ordinal = 0;
-  CGCN_TRY(validate(m, false));
-  cudaStream_t st = static_cast<cudaStream_t>(m->stream);
-  const int n = m->graph.n, d = m->d, S = m->strands, C = m->nclass, L = m->layers;
-  const int W = S * d;
-  const int64_t M = static_cast<int64_t>(n) * S;
-  const WsLayout lay = make_layout(n, d, C, L, S);
-  float* ws = m->workspace;
-  void* tcws = ws + lay.tc;
+// ------------------------------------------------------------------------------------------------
+// The model as stages.  cgcn_model_forward / _backward run them back to back on one GPU.  For one graph
+// row-partitioned over several GPUs (m->n_total > 0: graph.n local rows, global column indices) the host calls
+// cgcn_model_phase() stage by stage and performs the exchange step in between: an all-gather of the panel the
+// next SpMM gathers from (into m->x_full), or an all-reduce of the BatchNorm sums (m->bn_sums).
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  const cgcn_model* m;
+  WsLayout lay;
+  cudaStream_t st;
+  int n, d, S, C, L, W;
+  int64_t M, n_total;
+  bool dist;
+  float* ws;
+  void* tcws;
+  unsigned long long drop_off;      // float4 offset of the first local row in the global panel
+};
 
-  for (int l = 0; l < L; ++l) {
-    const float* xin = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
-    // ax = A_hat x                                   (torch.spmm, models/SubLayers.py:46)
-    CGCN_TRY(spmm_launch(&m->graph, xin, ws + lay.ax[l], W, 1, nullptr, st));
-    // y = ax W + b                                   (torch.mm + bias, models/SubLayers.py:43,50)
-    CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.ax[l], d, m->params.gc_w[l], 0, m->params.gc_b[l], ws + lay.z[l], d, M, d, d,
-                                    nullptr, nullptr, 1, m->gemm_impl, tcws, lay.tc_bytes, st));
-    // z = tanh(y); g = sigmoid(W z); x' = (1-g) x + g z; dropout between the layers
-    //                                                (models/ChromeModels.py:38-42 / 44-46)
-    GateFwdArgs a{};
-    a.y = ws + lay.z[l];
-    a.x = xin;
-    a.wg = m->params.gate_w[l];
-    a.bg = m->params.gate_b[l];
-    a.z = ws + lay.z[l];
-    a.g = m->gate[l];
-    a.xo = ws + lay.xo[l];
-    a.stats_partial = ws + lay.partial;
-    a.n = n;
-    const bool last = (l == L - 1);
-    a.drop = make_dropout(m->dropout_p, m->seed, m->step, 0, m->training && !last);
-    int grid = 0;
-    CGCN_TRY(gate_fwd_launch(a, d, S, last && m->training, &grid, st));
-    if (last)
-      CGCN_TRY(bn_finalize_launch(ws + lay.partial, grid, n, S, d, m->bn_eps, m->bn_momentum, m->training,
+static Ctx make_ctx(const cgcn_model* m) {
+  Ctx c;
+  c.m = m;
+  c.st = static_cast<cudaStream_t>(m->stream);
+  c.n = m->graph.n; c.d = m->d; c.S = m->strands; c.C = m->nclass; c.L = m->layers;
+  c.W = c.S * c.d;
+  c.M = static_cast<int64_t>(c.n) * c.S;
+  c.dist = m->n_total > 0;
+  c.n_total = c.dist ? m->n_total : c.n;
+  c.lay = make_layout(c.n, c.d, c.C, c.L, c.S);
+  c.ws = m->workspace;
+  c.tcws = c.ws + c.lay.tc;
+  c.drop_off = c.dist ? static_cast<unsigned long long>(m->row_begin) * c.W / 4 : 0ull;
+  return c;
+}
+
+// layer l: ax = A_hat x ; y = ax W + b ; gate.  `gather_src` is the panel the SpMM reads neighbours from (the
+// layer input itself on one GPU, the all-gathered copy of it when row-partitioned).
+static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
+  const cgcn_model* m = c.m;
+  const WsLayout& lay = c.lay;
+  float* ws = c.ws;
+  const float* xin = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
+  // ax = A_hat x                                   (torch.spmm, models/SubLayers.py:46)
+  CGCN_TRY(spmm_launch(&m->graph, gather_src, ws + lay.ax[l], c.W, 1, nullptr, c.st));
+  // y = ax W + b                                   (torch.mm + bias, models/SubLayers.py:43,50)
+  CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.ax[l], c.d, m->params.gc_w[l], 0, m->params.gc_b[l], ws + lay.z[l], c.d, c.M, c.d,
+                                  c.d, nullptr, nullptr, 1, m->gemm_impl, c.tcws, lay.tc_bytes, c.st));
+  // z = tanh(y); g = sigmoid(W z); x' = (1-g) x + g z; dropout between the layers
+  //                                                (models/ChromeModels.py:38-42 / 44-46)
+  GateFwdArgs a{};
+  a.y = ws + lay.z[l];
+  a.x = xin;
+  a.wg = m->params.gate_w[l];
+  a.bg = m->params.gate_b[l];
+  a.z = ws + lay.z[l];
+  a.g = m->gate[l];
+  a.xo = ws + lay.xo[l];
+  a.stats_partial = ws + lay.partial;
+  a.n = c.n;
+  const bool last = (l == c.L - 1);
+  a.drop = make_dropout(m->dropout_p, m->seed, m->step, 0, m->training && !last, c.drop_off);
+  int grid = 0;
+  CGCN_TRY(gate_fwd_launch(a, c.d, c.S, last && m->training, &grid, c.st));
+  if (last) {
+    if (c.dist && m->training)       // publish this rank's column sums; the host all-reduces m->bn_sums
+      CGCN_TRY(bn_finalize_launch(ws + lay.partial, grid, c.n_total, c.S, c.d, m->bn_eps, m->bn_momentum, 1, m->bn_running_mean,
+                                  m->bn_running_var, nullptr, ws + lay.bn_mean, ws + lay.bn_rstd, nullptr, m->bn_sums, c.st));
+    else if (!c.dist)
+      CGCN_TRY(bn_finalize_launch(ws + lay.partial, grid, c.n, c.S, c.d, m->bn_eps, m->bn_momentum, m->training,
                                   m->bn_running_mean, m->bn_running_var, m->bn_num_batches_tracked, ws + lay.bn_mean,
-                                  ws + lay.bn_rstd, st));
+                                  ws + lay.bn_rstd, nullptr, nullptr, c.st));
   }
+  return CGCN_OK;
+}
+
+static int fwd_head(const Ctx& c) {
+  const cgcn_model* m = c.m;
+  const WsLayout& lay = c.lay;
+  float* ws = c.ws;
+  if (c.dist)                        // statistics from the all-reduced sums (or the running stats in eval mode)
+    CGCN_TRY(bn_finalize_launch(ws + lay.partial, 0, c.n_total, c.S, c.d, m->bn_eps, m->bn_momentum, m->training,
+                                m->bn_running_mean, m->bn_running_var, m->bn_num_batches_tracked, ws + lay.bn_mean,
+                                ws + lay.bn_rstd, m->training ? m->bn_sums : nullptr, nullptr, c.st));
   // hb = dropout(BatchNorm(relu(x)))                 (models/ChromeModels.py:48-50)
   BnApplyArgs b{};
-  b.h = ws + lay.xo[L - 1];
+  b.h = ws + lay.xo[c.L - 1];
   b.mean = ws + lay.bn_mean;
   b.rstd = ws + lay.bn_rstd;
   b.gamma = m->params.bn_w;
   b.beta = m->params.bn_b;
   b.hb = ws + lay.hb;
-  b.total4 = static_cast<int64_t>(n) * W / 4;
-  b.S = S;
-  b.D = d;
-  b.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training);
-  CGCN_TRY(bn_apply_launch(b, st));
+  b.total4 = static_cast<int64_t>(c.n) * c.W / 4;
+  b.S = c.S;
+  b.D = c.d;
+  b.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training, c.drop_off);
+  CGCN_TRY(bn_apply_launch(b, c.st));
   // out = hb Wout^T + bout                           (models/ChromeModels.py:51)
-  const int ldo = m->out_ld > 0 ? m->out_ld : C;
-  CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.hb, d, m->params.out_w, 1, m->params.out_b, m->out, ldo, M, C, d, nullptr, nullptr, 1,
-                                  m->gemm_impl, tcws, lay.tc_bytes, st));
+  const int ldo = m->out_ld > 0 ? m->out_ld : c.C;
+  return gemm_rowpanel_dispatch(ws + lay.hb, c.d, m->params.out_w, 1, m->params.out_b, m->out, ldo, c.M, c.C, c.d, nullptr, nullptr,
+                                1, m->gemm_impl, c.tcws, lay.tc_bytes, c.st);
+}
+
+static int model_forward(const cgcn_model* m) {
+  tls_rp_ordinal = tls_gr_ordinal = 0;
+  CGCN_TRY(validate(m, false));
+  CGCN_REQUIRE(m->n_total <= 0, "cgcn_model_forward: row-partitioned graphs (n_total > 0) run through cgcn_model_phase");
+  const Ctx c = make_ctx(m);
+  for (int l = 0; l < c.L; ++l) CGCN_TRY(fwd_layer(c, l, (l == 0) ? m->x_in : c.ws + c.lay.xo[l - 1]));
+  return fwd_head(c);
+}
+
+// ---- backward stages.  Four scratch panels: `src` (gradient entering a gate stage), dy, dxd and the SpMM output;
+// dy is never written by the main stream while the side stream's gram kernel reads it.
+//   layer L-1: src = dA, dy = dB, dxd = dC, t -> dA, dx -> dD ;  layer L-2: src = dD, dy = dA, dxd = dC, t -> dD
+struct Fork {
+  SideStream* side;
+  cudaStream_t st, ss;
+  bool serial;
+  int id = 0;
+  int fork() {                       // side stream waits for everything enqueued on `st` so far
+    if (serial) return CGCN_OK;
+    CGCN_CUDA(cudaEventRecord(side->fork[id], st));
+    CGCN_CUDA(cudaStreamWaitEvent(ss, side->fork[id], 0));
+    id = (id + 1) & 3;
+    return CGCN_OK;
+  }
+  int join() {                       // the caller's stream owns every gradient again
+    if (serial) return CGCN_OK;
+    CGCN_CUDA(cudaEventRecord(side->join, ss));
+    CGCN_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    return CGCN_OK;
+  }
+};
+
+static int make_fork(const Ctx& c, Fork* f) {
+  static const bool no_side = getenv("CGCN_NO_SIDE_STREAM") != nullptr;   // developer aid
+  f->serial = no_side;
+  f->st = c.st;
+  f->side = nullptr;
+  f->ss = c.st;
+  if (!f->serial) {
+    CGCN_TRY(side_stream(&f->side));
+    f->ss = f->side->stream;
+  }
+  return CGCN_OK;
+}
+
+// head: side: d out.weight = dout^T hb ; d out.bias = colsum(dout).  main: d hb = dout Wout ; BatchNorm backward sums
+static int bwd_head(const Ctx& c, Fork& f) {
+  const cgcn_model* m = c.m;
+  const WsLayout& lay = c.lay;
+  float* ws = c.ws;
+  float* dA = ws + lay.dA;
+  void* gram_ws = ws + lay.gram;               // used by the side stream only
+  const int ldo = m->out_ld > 0 ? m->out_ld : c.C;
+  CGCN_TRY(f.fork());
+  CGCN_TRY(gemm_gram_dispatch(m->out_grad, ldo, ws + lay.hb, c.d, m->grads.out_w, c.d, c.M, c.C, c.d, 0, m->gemm_impl, gram_ws,
+                              lay.gram_bytes, f.ss));
+  CGCN_TRY(colsum_launch(m->out_grad, c.M, c.C, ldo, m->grads.out_b, ws + lay.partial_side, f.ss));
+  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, ldo, m->params.out_w, 0, nullptr, dA, c.d, c.M, c.d, c.C, nullptr, nullptr, 1,
+                                  m->gemm_impl, c.tcws, lay.tc_bytes, c.st));
+  BnBwdReduceArgs r{};
+  r.dhb = dA;
+  r.h = ws + lay.xo[c.L - 1];
+  r.mean = ws + lay.bn_mean;
+  r.rstd = ws + lay.bn_rstd;
+  r.partial = ws + lay.partial;
+  r.n = c.n;
+  r.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training, c.drop_off);
+  int grid = 0;
+  CGCN_TRY(bn_bwd_reduce_launch(r, c.d, c.S, &grid, c.st));
+  // one GPU: c1, c2, d gamma, d beta.  Row-partitioned: local d gamma / d beta + this rank's sums into m->bn_sums
+  return bn_bwd_finalize_launch(ws + lay.partial, grid, c.n_total, c.S, c.d, m->training, ws + lay.bn_c1, ws + lay.bn_c2,
+                                m->grads.bn_w, m->grads.bn_b, nullptr, c.dist ? m->bn_sums : nullptr, c.st);
+}
+
+static const float* bwd_src(const Ctx& c, int l) { return c.ws + ((l == c.L - 1) ? c.lay.dA : c.lay.dD); }
+static float* bwd_dy(const Ctx& c, int l) { return c.ws + ((l == c.L - 1) ? c.lay.dB : c.lay.dA); }
+
+// dx of layer l+1's input = dxd + P t, with t gathered from `t_gather` (layer l+1's t, or its all-gathered copy)
+static int bwd_propagate(const Ctx& c, int l_from, const float* t_gather) {
+  float* dx = (l_from == 0) ? c.m->x_in_grad : c.ws + c.lay.dD;
+  return spmm_launch(&c.m->graph, t_gather, dx, c.W, 0, c.ws + c.lay.dC, c.st);
+}
+
+// gate stage of layer l, its weight gradients (side stream) and, if anything upstream needs it, t = D^-1 (dy W^T).
+// Returns in *t_out the panel holding t (NULL if the chain stops here).
+static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out) {
+  const cgcn_model* m = c.m;
+  const WsLayout& lay = c.lay;
+  float* ws = c.ws;
+  const bool head = (l == c.L - 1);
+  const bool need_dx = (l > 0) || m->need_input_grad;
+  const float* src = bwd_src(c, l);
+  float* dy = bwd_dy(c, l);
+  *t_out = nullptr;
+  if (head && c.dist)                // c1, c2 from the all-reduced BatchNorm backward sums
+    CGCN_TRY(bn_bwd_finalize_launch(ws + lay.partial, 0, c.n_total, c.S, c.d, m->training, ws + lay.bn_c1, ws + lay.bn_c2, nullptr,
+                                    nullptr, m->bn_sums, nullptr, c.st));
+  GateBwdArgs a{};
+  a.dsrc = src;
+  a.h = ws + lay.xo[l];
+  a.mean = ws + lay.bn_mean;
+  a.rstd = ws + lay.bn_rstd;
+  a.gamma = m->params.bn_w;
+  a.c1 = ws + lay.bn_c1;
+  a.c2 = ws + lay.bn_c2;
+  a.z = ws + lay.z[l];
+  a.x = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
+  a.g = m->gate[l];
+  a.wg = m->params.gate_w[l];
+  a.dy = dy;
+  a.dxd = need_dx ? ws + lay.dC : nullptr;
+  a.partial = ws + lay.partial_l[l];
+  a.n = c.n;
+  a.drop = make_dropout(m->dropout_p, m->seed, m->step, head ? 1 : 0, m->training, c.drop_off);
+  int grid = 0;
+  CGCN_TRY(gate_bwd_launch(a, c.d, c.S, head, &grid, c.st));
+  // side: bias / gate gradients from the partials, d W = (A_hat x)^T dy
+  CGCN_TRY(f.fork());
+  CGCN_TRY(gate_bwd_finalize_launch(ws + lay.partial_l[l], grid, c.d, m->grads.gc_b[l], m->grads.gate_w[l], m->grads.gate_b[l], f.ss));
+  CGCN_TRY(gemm_gram_dispatch(ws + lay.ax[l], c.d, dy, c.d, m->grads.gc_w[l], c.d, c.M, c.d, c.d, 0, m->gemm_impl, ws + lay.gram,
+                              lay.gram_bytes, f.ss));
+  if (!need_dx) return CGCN_OK;
+  // main: t = D^-1 (dy W^T) -> the panel that held `src`
+  float* t = const_cast<float*>(src);
+  CGCN_TRY(gemm_rowpanel_dispatch(dy, c.d, m->params.gc_w[l], 1, nullptr, t, c.d, c.M, c.d, c.d, m->graph.rowptr, m->graph.row_inv, c.S,
+                                  m->gemm_impl, c.tcws, lay.tc_bytes, c.st));
+  *t_out = t;
   return CGCN_OK;
 }
 
 static int model_backward(const cgcn_model* m) {
   CGCN_TRY(validate(m, true));
-  cudaStream_t st = static_cast<cudaStream_t>(m->stream);
-  SideStream* side = nullptr;
-  CGCN_TRY(side_stream(&side));
-  cudaStream_t ss = side->stream;
-  static const bool serial = getenv("CGCN_NO_SIDE_STREAM") != nullptr;   // developer aid: everything on the caller's stream
-  if (serial) ss = st;
-  const int n = m->graph.n, d = m->d, S = m->strands, C = m->nclass, L = m->layers;
-  const int W = S * d;
-  const int64_t M = static_cast<int64_t>(n) * S;
-  const WsLayout lay = make_layout(n, d, C, L, S);
-  float* ws = m->workspace;
-  void* tcws = ws + lay.tc;
-  float* dA = ws + lay.dA;
-  float* dB = ws + lay.dB;
-  float* dC = ws + lay.dC;
-  float* dD = ws + lay.dD;
-  void* gram_ws = ws + lay.gram;               // used by the side stream only
-  int fork_id = 0;
-  auto fork = [&]() -> int {                    // side stream waits for everything enqueued on `st` so far
-    if (serial) return CGCN_OK;
-    CGCN_CUDA(cudaEventRecord(side->fork[fork_id], st));
-    CGCN_CUDA(cudaStreamWaitEvent(ss, side->fork[fork_id], 0));
-    fork_id = (fork_id + 1) & 3;
-    return CGCN_OK;
-  };
+  CGCN_REQUIRE(m->n_total <= 0, "cgcn_model_backward: row-partitioned graphs (n_total > 0) run through cgcn_model_phase");
+  const Ctx c = make_ctx(m);
+  Fork f;
+  CGCN_TRY(make_fork(c, &f));
+  CGCN_TRY(bwd_head(c, f));
+  for (int l = c.L - 1; l >= 0; --l) {
+    const float* t = nullptr;
+    CGCN_TRY(bwd_layer(c, f, l, &t));
+    if (t == nullptr) break;
+    CGCN_TRY(bwd_propagate(c, l, t));
+  }
+  return f.join();
+}
 
-  // head.  side: d out.weight = dout^T hb ; d out.bias = colsum(dout).   main: d hb = dout Wout
-  const int ldo = m->out_ld > 0 ? m->out_ld : C;
-  CGCN_TRY(fork());
-  CGCN_TRY(gemm_gram_dispatch(m->out_grad, ldo, ws + lay.hb, d, m->grads.out_w, d, M, C, d, 0, m->gemm_impl, gram_ws,
-                              lay.gram_bytes, ss));
-  CGCN_TRY(colsum_launch(m->out_grad, M, C, ldo, m->grads.out_b, ws + lay.partial_side, ss));
-  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, ldo, m->params.out_w, 0, nullptr, dA, d, M, d, C, nullptr, nullptr, 1, m->gemm_impl,
-                                  tcws, lay.tc_bytes, st));
-  // BatchNorm backward sums (needed by the next kernel: stays on the main stream)
-  {
-    BnBwdReduceArgs r{};
-    r.dhb = dA;
-    r.h = ws + lay.xo[L - 1];
-    r.mean = ws + lay.bn_mean;
-    r.rstd = ws + lay.bn_rstd;
-    r.partial = ws + lay.partial;
-    r.n = n;
-    r.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training);
-    int grid = 0;
-    CGCN_TRY(bn_bwd_reduce_launch(r, d, S, &grid, st));
-    CGCN_TRY(bn_bwd_finalize_launch(ws + lay.partial, grid, n, S, d, m->training, ws + lay.bn_c1, ws + lay.bn_c2,
-                                    m->grads.bn_w, m->grads.bn_b, st));
+// One stage of the row-partitioned model.  *publish (may be NULL) receives the local panel the host must
+// all-gather into m->x_full before the next stage, or NULL when the next stage needs no gather.
+static int model_phase(const cgcn_model* m, int kind, int layer, const float** publish) {
+  if (publish) *publish = nullptr;
+  CGCN_TRY(validate(m, kind >= CGCN_PHASE_BWD_HEAD));
+  CGCN_REQUIRE(m->n_total >= m->graph.n && m->x_full != nullptr && m->bn_sums != nullptr && m->row_begin >= 0,
+               "cgcn_model_phase: needs n_total, row_begin, x_full and bn_sums");
+  CGCN_REQUIRE(layer >= 0 && layer < m->layers, "cgcn_model_phase: layer %d", layer);
+  const Ctx c = make_ctx(m);
+  Fork f;
+  f.serial = true;                   // stage by stage: everything on the caller's stream
+  f.st = f.ss = c.st;
+  f.side = nullptr;
+  const float* t = nullptr;
+  switch (kind) {
+    case CGCN_PHASE_FWD_LAYER:       // x_full holds the gathered input of `layer`
+      if (layer == 0) tls_rp_ordinal = tls_gr_ordinal = 0;
+      CGCN_TRY(fwd_layer(c, layer, m->x_full));
+      if (publish && layer + 1 < c.L) *publish = c.ws + c.lay.xo[layer];
+      return CGCN_OK;
+    case CGCN_PHASE_FWD_HEAD:        // bn_sums all-reduced
+      return fwd_head(c);
+    case CGCN_PHASE_BWD_HEAD:
+      return bwd_head(c, f);
+    case CGCN_PHASE_BWD_LAYER:       // layer == L-1: bn_sums all-reduced ; else: x_full holds the gathered t of layer+1
+      if (layer < c.L - 1) CGCN_TRY(bwd_propagate(c, layer + 1, m->x_full));
+      CGCN_TRY(bwd_layer(c, f, layer, &t));
+      if (publish) *publish = t;
+      return CGCN_OK;
+    case CGCN_PHASE_BWD_INPUT:       // x_full holds the gathered t of layer 0
+      CGCN_REQUIRE(m->need_input_grad && m->x_in_grad, "cgcn_model_phase: BWD_INPUT without need_input_grad");
+      return bwd_propagate(c, 0, m->x_full);
+    default:
+      set_error("cgcn_model_phase: unknown phase %d", kind);
+      return CGCN_ERR_INVALID;
   }
-  // layers, last to first.  Four scratch panels: `src` (gradient entering the gate stage), dy, dxd, and the
-  // SpMM output; dy stays untouched by the main stream while the side stream's gram kernel reads it.
-  //   layer L-1: src = dA, dy = dB, dxd = dC, t -> dA, dx -> dD
-  //   layer L-2: src = dD, dy = dA, dxd = dC, t -> dD, dx -> x_in_grad
-  const float* src = dA;
-  for (int l = L - 1; l >= 0; --l) {
-    const bool head = (l == L - 1);
-    const bool need_dx = (l > 0) || m->need_input_grad;
-    const float* xin = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
-    float* dy = (src == dA) ? dB : dA;
-    float* dxd = dC;
-    GateBwdArgs a{};
-    a.dsrc = src;
-    a.h = ws + lay.xo[l];
-    a.mean = ws + lay.bn_mean;
-    a.rstd = ws + lay.bn_rstd;
-    a.gamma = m->params.bn_w;
-    a.c1 = ws + lay.bn_c1;
-    a.c2 = ws + lay.bn_c2;
-    a.z = ws + lay.z[l];
-    a.x = xin;
-    a.g = m->gate[l];
-    a.wg = m->params.gate_w[l];
-    a.dy = dy;
-    a.dxd = need_dx ? dxd : nullptr;
-    a.partial = ws + lay.partial_l[l];
-    a.n = n;
-    a.drop = head ? make_dropout(m->dropout_p, m->seed, m->step, 1, m->training)
-                  : make_dropout(m->dropout_p, m->seed, m->step, 0, m->training);
-    int grid = 0;
-    CGCN_TRY(gate_bwd_launch(a, d, S, head, &grid, st));
-    // side: bias / gate gradients from the partials, d W = (A_hat x)^T dy
-    CGCN_TRY(fork());
-    CGCN_TRY(gate_bwd_finalize_launch(ws + lay.partial_l[l], grid, d, m->grads.gc_b[l], m->grads.gate_w[l],
-                                      m->grads.gate_b[l], ss));
-    CGCN_TRY(gemm_gram_dispatch(ws + lay.ax[l], d, dy, d, m->grads.gc_w[l], d, M, d, d, 0, m->gemm_impl, gram_ws,
-                                lay.gram_bytes, ss));
-    if (!need_dx) break;
-    // main: t = D^-1 (dy W^T) -> the panel that held `src` ; then dx = dxd + P t
-    float* t = const_cast<float*>(src);
-    CGCN_TRY(gemm_rowpanel_dispatch(dy, d, m->params.gc_w[l], 1, nullptr, t, d, M, d, d, m->graph.rowptr, m->graph.row_inv, S, m->gemm_impl,
-                                    tcws, lay.tc_bytes, st));
-    float* dx = (l == 0) ? m->x_in_grad : dD;
-    CGCN_TRY(spmm_launch(&m->graph, t, dx, W, 0, dxd, st));
-    src = dx;
-  }
-  if (!serial) {                                // join: the caller's stream owns every gradient again
-    CGCN_CUDA(cudaEventRecord(side->join, ss));
-    CGCN_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-  }
-  return CGCN_OK;
 }
 
 }  // namespace cgcn
@@ -422,6 +545,9 @@ extern "C" size_t cgcn_model_workspace_bytes(int32_t n, int32_t d, int32_t nclas
 }
 
 extern "C" int cgcn_model_forward(const cgcn_model* m) { return model_forward(m); }
+extern "C" int cgcn_model_phase(const cgcn_model* m, int32_t kind, int32_t layer, const float** publish) {
+  return model_phase(m, kind, layer, publish);
+}
 extern "C" int cgcn_model_backward(const cgcn_model* m) { return model_backward(m); }
 
 extern "C" int cgcn_train_step(const cgcn_model* m, const float* target, float* probs, float* loss_sum_out,
@@ -430,7 +556,7 @@ extern "C" int cgcn_train_step(const cgcn_model* m, const float* target, float* 
   CGCN_TRY(model_forward(m));
   const WsLayout lay = make_layout(m->graph.n, m->d, m->nclass, m->layers, m->strands);
   CGCN_TRY(bce_launch(m->out, target, m->graph.n, m->nclass, m->strands, m->out_ld > 0 ? m->out_ld : m->nclass, probs,
-                      loss_sum_out, out_grad_scratch, m->workspace + lay.partial, static_cast<cudaStream_t>(m->stream)));
+                      loss_sum_out, out_grad_scratch, m->workspace + lay.partial, 0, static_cast<cudaStream_t>(m->stream)));
   cgcn_model mb = *m;
   mb.out_grad = out_grad_scratch;
   return model_backward(&mb);

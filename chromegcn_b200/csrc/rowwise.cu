@@ -158,9 +158,10 @@ __global__ void __launch_bounds__(RW_THREADS) gate_fwd_kernel(const GateFwdArgs 
 // variance (torch.nn.BatchNorm1d semantics).  Eval mode: running stats.
 template <int S>
 __global__ void __launch_bounds__(32 * FIN_SLICES)
-bn_finalize_kernel(const float* __restrict__ partial, int parts, int n, int D, float eps, float momentum, int training,
+bn_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, int D, float eps, float momentum, int training,
                    float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ num_batches,
-                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out, const double* __restrict__ presummed,
+                   double* __restrict__ sums_out) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool active = c < D;
   const int K = 2 * S * D;
@@ -182,8 +183,18 @@ bn_finalize_kernel(const float* __restrict__ partial, int parts, int n, int D, f
     offs[2 * s + 1] = (1 * S + s) * D + c;
   }
   double sums[2 * S];
-  reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
+  if (presummed != nullptr) {                       // row-partitioned mode: sums already reduced over CTAs and ranks
+#pragma unroll
+    for (int v = 0; v < 2 * S; ++v) sums[v] = active ? presummed[offs[v]] : 0.0;
+  } else {
+    reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
+  }
   if (!active || threadIdx.y != 0) return;
+  if (sums_out != nullptr) {                        // row-partitioned mode, first half: publish this rank's sums
+#pragma unroll
+    for (int v = 0; v < 2 * S; ++v) sums_out[offs[v]] = sums[v];
+    return;
+  }
   float rm = running_mean[c], rv = running_var[c];
 #pragma unroll
   for (int s = 0; s < S; ++s) {
@@ -269,8 +280,9 @@ __global__ void __launch_bounds__(RW_THREADS, (DV == 1) ? 4 : 1) bn_bwd_reduce_k
 // d gamma = sum_s sum dbn*xhat ; d beta = sum_s sum dbn.
 template <int S>
 __global__ void __launch_bounds__(32 * FIN_SLICES)
-bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int n, int D, int training, float* __restrict__ c1,
-                       float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, int D, int training, float* __restrict__ c1,
+                       float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       const double* __restrict__ presummed, double* __restrict__ sums_out) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool active = c < D;
   const int K = 2 * S * D;
@@ -281,13 +293,32 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int n, int 
     offs[2 * s + 1] = (1 * S + s) * D + c;
   }
   double sums[2 * S];
-  reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
+  if (presummed != nullptr) {
+#pragma unroll
+    for (int v = 0; v < 2 * S; ++v) sums[v] = active ? presummed[offs[v]] : 0.0;
+  } else {
+    reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
+  }
   if (!active || threadIdx.y != 0) return;
+  if (presummed != nullptr) {                       // second half: c1 / c2 from the all-reduced sums; d gamma / d beta stay local
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      c1[s * D + c] = training ? static_cast<float>(sums[2 * s] / n) : 0.f;
+      c2[s * D + c] = training ? static_cast<float>(sums[2 * s + 1] / n) : 0.f;
+    }
+    return;
+  }
+  if (sums_out != nullptr) {
+#pragma unroll
+    for (int v = 0; v < 2 * S; ++v) sums_out[offs[v]] = sums[v];
+  }
   double tg = 0.0, tb = 0.0;
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    c1[s * D + c] = training ? static_cast<float>(sums[2 * s] / n) : 0.f;
-    c2[s * D + c] = training ? static_cast<float>(sums[2 * s + 1] / n) : 0.f;
+    if (sums_out == nullptr) {
+      c1[s * D + c] = training ? static_cast<float>(sums[2 * s] / n) : 0.f;
+      c2[s * D + c] = training ? static_cast<float>(sums[2 * s + 1] / n) : 0.f;
+    }
     tb += sums[2 * s];
     tg += sums[2 * s + 1];
   }
@@ -608,16 +639,16 @@ int gate_fwd_launch(const GateFwdArgs& a, int d, int S, bool stats, int* grid_ou
   return check_launch("gate_fwd_kernel");
 }
 
-int bn_finalize_launch(const float* partial, int parts, int n, int S, int D, float eps, float momentum, int training,
+int bn_finalize_launch(const float* partial, int parts, int64_t n, int S, int D, float eps, float momentum, int training,
                        float* running_mean, float* running_var, int64_t* nbt, float* mean_out, float* rstd_out,
-                       cudaStream_t stream) {
+                       const double* presummed, double* sums_out, cudaStream_t stream) {
   const dim3 blk(32, FIN_SLICES);
   if (S == 1)
     bn_finalize_kernel<1><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, eps, momentum, training, running_mean,
-                                                             running_var, nbt, mean_out, rstd_out);
+                                                             running_var, nbt, mean_out, rstd_out, presummed, sums_out);
   else
     bn_finalize_kernel<2><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, eps, momentum, training, running_mean,
-                                                             running_var, nbt, mean_out, rstd_out);
+                                                             running_var, nbt, mean_out, rstd_out, presummed, sums_out);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -639,13 +670,15 @@ int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, 
   return check_launch("bn_bwd_reduce_kernel");
 }
 
-int bn_bwd_finalize_launch(const float* partial, int parts, int n, int S, int D, int training, float* c1, float* c2,
-                           float* dgamma, float* dbeta, cudaStream_t stream) {
+int bn_bwd_finalize_launch(const float* partial, int parts, int64_t n, int S, int D, int training, float* c1, float* c2,
+                           float* dgamma, float* dbeta, const double* presummed, double* sums_out, cudaStream_t stream) {
   const dim3 blk(32, FIN_SLICES);
   if (S == 1)
-    bn_bwd_finalize_kernel<1><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, training, c1, c2, dgamma, dbeta);
+    bn_bwd_finalize_kernel<1><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, training, c1, c2, dgamma, dbeta,
+                                                                 presummed, sums_out);
   else
-    bn_bwd_finalize_kernel<2><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, training, c1, c2, dgamma, dbeta);
+    bn_bwd_finalize_kernel<2><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, training, c1, c2, dgamma, dbeta,
+                                                                 presummed, sums_out);
   return check_launch("bn_bwd_finalize_kernel");
 }
 
@@ -709,9 +742,10 @@ int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* dst, fl
 int bce_grid() { return sm_count() * 8; }
 
 int bce_launch(const float* out, const float* target, int n, int C, int S, int ld, float* probs, float* loss_sum,
-               float* out_grad, float* partial, cudaStream_t stream) {
+               float* out_grad, float* partial, int64_t n_total, cudaStream_t stream) {
+  if (n_total <= 0) n_total = n;                       // row-partitioned graphs normalise by the global row count
   BceArgs a{out, target, probs, out_grad, partial, static_cast<int64_t>(n) * ld, C, S, ld,
-            static_cast<float>(1.0 / (static_cast<double>(n) * C))};
+            static_cast<float>(1.0 / (static_cast<double>(n_total) * C))};
   CGCN_REQUIRE(a.total * S < 4294967296LL, "cgcn_bce_loss: n * nclass * strands must fit 32 bits");
   int grid = static_cast<int>((a.total + 1023) / 1024);
   if (grid > bce_grid()) grid = bce_grid();
@@ -734,8 +768,8 @@ extern "C" size_t cgcn_bce_workspace_bytes(int32_t n, int32_t nclass) {
 }
 
 extern "C" int cgcn_bce_loss(const float* out, const float* target, int32_t n, int32_t nclass, int32_t strands,
-                             int32_t out_ld, float* probs, float* loss_sum_out, float* out_grad, void* workspace,
-                             size_t workspace_bytes, cgcn_stream_t stream) {
+                             int32_t out_ld, int64_t n_total, float* probs, float* loss_sum_out, float* out_grad,
+                             void* workspace, size_t workspace_bytes, cgcn_stream_t stream) {
   CGCN_REQUIRE(out && target && loss_sum_out, "cgcn_bce_loss: null argument");
   CGCN_REQUIRE(n >= 1 && nclass >= 1 && (strands == 1 || strands == 2), "cgcn_bce_loss: bad shape");
   if (out_ld <= 0) out_ld = nclass;
@@ -745,7 +779,7 @@ extern "C" int cgcn_bce_loss(const float* out, const float* target, int32_t n, i
     return CGCN_ERR_WORKSPACE;
   }
   return bce_launch(out, target, n, nclass, strands, out_ld, probs, loss_sum_out, out_grad,
-                    static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+                    static_cast<float*>(workspace), n_total, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cgcn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t count, float lr,

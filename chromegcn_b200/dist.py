@@ -123,3 +123,110 @@ def allgather_panel(local: torch.Tensor, parts: Sequence[Tuple[int, int]], out: 
     for r, (b, e) in enumerate(parts):
         out[b:e] = recv[r, : e - b]
     return out
+
+
+# ------------------------------------------------------------------ row-partitioned train step (one huge graph)
+PHASE_FWD_LAYER, PHASE_FWD_HEAD, PHASE_BWD_HEAD, PHASE_BWD_LAYER, PHASE_BWD_INPUT = 0, 1, 2, 3, 4
+
+
+class RowPartitionedStep:
+    """One chromosome too large for (or simply spread over) several GPUs: rank r owns the contiguous row block
+    `parts[r]` of every panel, its rows of the CSR pattern (global column indices) and a replica of the
+    parameters.  `run()` drives `cgcn_model_phase` stage by stage and performs the exchange steps in between
+    (SURVEY.md 8(e)): all-gather of the panel the next SpMM reads (L forward + L-1 backward, +1 with input
+    gradients), all-reduce of the BatchNorm column sums (forward and backward), and one all-reduce of the flat
+    gradient buffer + loss at the end.  With world_size 1 the collectives are identities and the result is the
+    single-GPU step."""
+
+    def __init__(self, model, graph_local, parts: Sequence[Tuple[int, int]], rank: int, strands: int = 2, group=None):
+        from .engine import ChromosomeEngine
+        self.model, self.graph, self.parts, self.rank, self.S, self.group = model, graph_local, list(parts), rank, strands, group
+        self.engine = ChromosomeEngine(model, strands)
+        self.n_total = parts[-1][1]
+        self.n_local = parts[rank][1] - parts[rank][0]
+        assert graph_local.n == self.n_local
+
+    def _gather(self, local_panel: torch.Tensor, x_full: torch.Tensor) -> None:
+        w = x_full.shape[1]
+        allgather_panel(local_panel.reshape(self.n_local, w), self.parts, out=x_full, group=self.group)
+
+    def _allreduce(self, t: torch.Tensor) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def run(self, panel_local: torch.Tensor, target_local: torch.Tensor, loss_out: torch.Tensor, train: bool = True,
+            probs_out: torch.Tensor = None, input_grad: torch.Tensor = None):
+        """panel_local `[n_local, S, d]`, target_local `[n_local, C]`; returns local logits `[n_local, S, C]`.
+        `loss_out[0]` receives the GLOBAL mean loss (all-reduced); gradients (all-reduced) land in the model's
+        flat gradient buffer."""
+        import ctypes as C
+        from . import _lib, ops
+        from .chrome_models import build_model_struct, padded_classes
+        from .engine import flat_params
+        lib = _lib.load()
+        model, eng, S = self.model, self.engine, self.S
+        fp = flat_params(model, full=False)
+        n, d = self.n_local, panel_local.shape[-1]
+        nclass, layers = model.out.out_features, model.num_layers
+        ld = padded_classes(nclass)
+        dev = panel_local.device
+        W = S * d
+        with torch.cuda.device(dev):
+            ws_bytes = lib.cgcn_model_workspace_bytes(n, d, nclass, layers, S)
+            ws = eng._buf("ws", ws_bytes // 4)
+            out = eng._buf("out", n * S * ld)[: n * S * ld].view(n, S, ld)
+            dout = eng._buf("dout", n * S * ld)[: n * S * ld].view(n, S, ld)
+            gates = [eng._buf("gate%d" % l, n * S)[: n * S].view(n, S) for l in range(layers)]
+            x_full = eng._buf("x_full", self.n_total * W)[: self.n_total * W].view(self.n_total, W)
+            bn_sums = eng._buf("bn_sums", 2 * S * d, dtype=torch.float64)[: 2 * S * d]
+            seed, step = model._next_dropout_counter() if model.training else (0, 0)
+            bn = model.batch_norm
+            m = build_model_struct(self.graph, d, nclass, layers, S, model.training, model.dropout, seed, step,
+                                   fp.views(fp.flat), fp.views(fp.flat_grad) if train else None, bn.running_mean,
+                                   bn.running_var, bn.num_batches_tracked, panel_local, input_grad, out, gates,
+                                   dout if train else None, ws, model.gemm_impl,
+                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld)
+            m.n_total, m.row_begin = self.n_total, self.parts[self.rank][0]
+            m.x_full, m.bn_sums = x_full.data_ptr(), bn_sums.data_ptr()
+            pub = C.c_void_p(0)
+
+            def phase(kind, layer=0):
+                m.stream = _lib.current_stream()
+                _lib.check(lib.cgcn_model_phase(C.byref(m), kind, layer, C.byref(pub)), "cgcn_model_phase(%d,%d)" % (kind, layer))
+                return pub.value
+
+            def gather_ptr(ptr):          # the published panel lives in the workspace: wrap it without copying
+                off = (ptr - ws.data_ptr()) // 4
+                self._gather(ws[off: off + n * W], x_full)
+
+            # ---- forward
+            self._gather(panel_local, x_full)
+            for l in range(layers):
+                p = phase(PHASE_FWD_LAYER, l)
+                if p:
+                    gather_ptr(p)
+            if model.training:
+                self._allreduce(bn_sums)
+            phase(PHASE_FWD_HEAD)
+            loss_local = torch.zeros(1, dtype=torch.float32, device=dev)
+            bce_ws = eng._buf("bce_ws", lib.cgcn_bce_workspace_bytes(n, nclass) // 4 + 64)
+            tgt = ops._f32c(target_local)
+            _lib.check(lib.cgcn_bce_loss(out.data_ptr(), tgt.data_ptr(), n, nclass, S, ld, self.n_total, _lib.ptr(probs_out),
+                                         loss_local.data_ptr(), dout.data_ptr() if train else None, bce_ws.data_ptr(),
+                                         bce_ws.numel() * 4, _lib.current_stream()), "cgcn_bce_loss")
+            self._allreduce(loss_local)
+            loss_out += loss_local
+            if not train:
+                return out[:, :, :nclass], gates
+            # ---- backward
+            phase(PHASE_BWD_HEAD)
+            self._allreduce(bn_sums)
+            for l in range(layers - 1, -1, -1):
+                p = phase(PHASE_BWD_LAYER, l)
+                if p:
+                    gather_ptr(p)
+            if input_grad is not None:
+                phase(PHASE_BWD_INPUT)
+            self._allreduce(fp.flat_grad)
+            fp.attach_grads()
+        return out[:, :, :nclass], gates

@@ -167,7 +167,7 @@ class ChromosomeEngine:
             else:
                 _lib.check(lib.cgcn_model_forward(C.byref(m)), "cgcn_model_forward")
                 bce_ws = self._buf("bce_ws", lib.cgcn_bce_workspace_bytes(n, nclass) // 4 + 64)
-                _lib.check(lib.cgcn_bce_loss(out.data_ptr(), tgt.data_ptr(), n, nclass, S, ld, _lib.ptr(probs_out),
+                _lib.check(lib.cgcn_bce_loss(out.data_ptr(), tgt.data_ptr(), n, nclass, S, ld, 0, _lib.ptr(probs_out),
                                              loss_slot.data_ptr(), None, bce_ws.data_ptr(), bce_ws.numel() * 4,
                                              _lib.current_stream()), "cgcn_bce_loss")
         self.step_count += 1

@@ -87,7 +87,7 @@ def gemm_gram(a: torch.Tensor, b: torch.Tensor, impl: int = GEMM_AUTO, out: Opti
 
 
 def bce_loss(out: torch.Tensor, target: torch.Tensor, strands: int, loss_acc: torch.Tensor,
-             want_probs: bool = True, want_grad: bool = True):
+             want_probs: bool = True, want_grad: bool = True, n_total: int = 0):
     """finetune.py:43-45,52 on `[n, strands, C]` logits: returns `(probs [n, C] | None, out_grad | None)`
     and adds the mean loss to `loss_acc[0]`."""
     lib = _lib.load()
@@ -99,7 +99,7 @@ def bce_loss(out: torch.Tensor, target: torch.Tensor, strands: int, loss_acc: to
     with torch.cuda.device(out.device):
         need = lib.cgcn_bce_workspace_bytes(n, c)
         ws = torch.empty(need, dtype=torch.uint8, device=out.device)
-        _lib.check(lib.cgcn_bce_loss(out.data_ptr(), target.data_ptr(), n, c, strands, ld, _lib.ptr(probs),
+        _lib.check(lib.cgcn_bce_loss(out.data_ptr(), target.data_ptr(), n, c, strands, ld, n_total, _lib.ptr(probs),
                                      loss_acc.data_ptr(), _lib.ptr(grad), ws.data_ptr(), need, _lib.current_stream()),
                    "cgcn_bce_loss")
     return probs, grad

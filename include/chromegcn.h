@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CGCN_ABI_VERSION 2
+#define CGCN_ABI_VERSION 3
 
 typedef void* cgcn_stream_t; /* cudaStream_t */
 
@@ -191,7 +191,7 @@ typedef struct cgcn_model {
   float dropout_p;        /* F.dropout p (models/ChromeModels.py:42,50) */
   float bn_momentum;      /* 0.1 */
   float bn_eps;           /* 1e-5 */
-  float reserved1;
+  int32_t row_begin;      /* row-partitioned graphs: global index of the first local row (dropout stream position) */
   uint64_t seed;          /* dropout: keep-mask is a pure function of (seed, step, site, element) */
   uint64_t step;
   cgcn_params params;
@@ -207,6 +207,12 @@ typedef struct cgcn_model {
   float* workspace;       /* cgcn_model_workspace_bytes() bytes, kept from forward to backward */
   size_t workspace_bytes;
   cgcn_stream_t stream;
+  /* One graph row-partitioned over several GPUs (cgcn_model_phase): graph.n = local rows, colidx = GLOBAL columns.
+   * n_total = global row count (0 = not partitioned), x_full = [n_total][strands][d] scratch the host all-gathers
+   * panels into, bn_sums = [2*strands*d] doubles the host all-reduces (BatchNorm column sums). */
+  int64_t n_total;
+  float* x_full;
+  double* bn_sums;
 } cgcn_model;
 
 size_t cgcn_model_workspace_bytes(int32_t n, int32_t d, int32_t nclass, int32_t layers, int32_t strands);
@@ -216,6 +222,19 @@ int cgcn_model_forward(const cgcn_model* m);
 int cgcn_model_backward(const cgcn_model* m);
 
 /*
+ * The same model stage by stage, for ONE graph row-partitioned over several GPUs (contiguous row blocks; the
+ * pattern is symmetric, so the same partition serves forward and backward).  Between stages the host performs
+ * the exchange step over NCCL:
+ *   all-gather x_in -> x_full ; FWD_LAYER(0) ; [all-gather *publish -> x_full ; FWD_LAYER(1)] ;
+ *   all-reduce bn_sums ; FWD_HEAD ; cgcn_bce_loss(n_total) ;
+ *   BWD_HEAD ; all-reduce bn_sums ; BWD_LAYER(L-1) ; [all-gather *publish -> x_full ; BWD_LAYER(L-2)] ;
+ *   [need_input_grad: all-gather *publish -> x_full ; BWD_INPUT] ; all-reduce the flat gradient buffer.
+ * *publish is the local panel to gather before the next stage (NULL if none).
+ */
+enum { CGCN_PHASE_FWD_LAYER = 0, CGCN_PHASE_FWD_HEAD = 1, CGCN_PHASE_BWD_HEAD = 2, CGCN_PHASE_BWD_LAYER = 3, CGCN_PHASE_BWD_INPUT = 4 };
+int cgcn_model_phase(const cgcn_model* m, int32_t kind, int32_t layer, const float** publish);
+
+/*
  * finetune.py:43-45,52: pred = mean over strands of the logits; loss = BCE-with-logits, mean over
  * n x nclass; probs = sigmoid(pred).  `out` and `out_grad` rows are out_ld floats apart (>= nclass).
  * Writes loss_sum_out[0] += loss (a device accumulator, like `total_loss += loss.item()` without the
@@ -223,6 +242,7 @@ int cgcn_model_backward(const cgcn_model* m);
  */
 size_t cgcn_bce_workspace_bytes(int32_t n, int32_t nclass);
 int cgcn_bce_loss(const float* out, const float* target, int32_t n, int32_t nclass, int32_t strands, int32_t out_ld,
+                  int64_t n_total /* rows the mean runs over; 0 = n (row-partitioned graphs pass the global count) */,
                   float* probs, float* loss_sum_out, float* out_grad,
                   void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
 

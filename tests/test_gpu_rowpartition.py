@@ -1,0 +1,112 @@
+"""GPU: one graph row-partitioned over ranks (cgcn_model_phase + exchange steps) equals the single-GPU step.
+
+* world_size 1 (always runs): the stage-by-stage path with identity collectives must reproduce
+  `ChromosomeEngine.run` bit for bit -- it is the same kernels in the same order;
+* world_size 2 (needs two GPUs, NCCL): contiguous row blocks, all-gather of the SpMM input panels, all-reduce of
+  the BatchNorm sums and of the flat gradient buffer; logits, loss and every gradient within 1e-5 of the
+  single-GPU result (only summation order differs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import adjacency as oadj
+from oracle import gcn as ogcn
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _case(device, dropout=0.0):
+    from chromegcn_b200.chrome_models import ChromeGCN
+    z = np.load(os.path.join(GOLDEN, "model_l2_stress.npz"))
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0.")}
+    m = ChromeGCN(128, 128, sd["out.weight"].shape[0], dropout, True, 2)
+    m.load_state_dict(sd)
+    m = m.to(device).train()
+    rp, ci = oadj.pattern_with_selfloops(z["indptr"], z["indices"])
+    return z, m, rp, ci
+
+
+def _single_gpu_reference(device, dropout=0.0, input_grad=True):
+    from chromegcn_b200.engine import ChromosomeEngine
+    from chromegcn_b200.graph import HiCGraph
+    z, m, rp, ci = _case(device, dropout)
+    g = HiCGraph.from_csr_pattern(rp, ci, device, add_selfloops=False)
+    eng = ChromosomeEngine(m, 2)
+    panel = eng.pack(torch.from_numpy(z["x_f"]).to(device), torch.from_numpy(z["x_r"]).to(device)).clone()
+    loss = torch.zeros(1, device=device)
+    xg = torch.empty_like(panel) if input_grad else None
+    out, _ = eng.run(g, panel, torch.from_numpy(z["target"]).to(device), None, loss, train=True, input_grad=xg)
+    return (out.clone(), loss.clone(), {k: p.grad.clone() for k, p in m.named_parameters()}, xg,
+            m.batch_norm.running_var.clone())
+
+
+def _partitioned(device, rank, world, dropout=0.0, input_grad=True, group=None):
+    from chromegcn_b200 import dist as cdist
+    from chromegcn_b200.graph import HiCGraph
+    from chromegcn_b200 import ops
+    z, m, rp, ci = _case(device, dropout)
+    n = rp.shape[0] - 1
+    parts = cdist.row_partition(n, world)
+    b, e = parts[rank]
+    lp, lc = cdist.local_rows_csr(rp, ci, b, e)
+    g = HiCGraph.from_csr_pattern(lp, lc, device, add_selfloops=False)
+    step = cdist.RowPartitionedStep(m, g, parts, rank, 2, group)
+    panel = ops.interleave_strands([torch.from_numpy(z["x_f"][b:e]).to(device), torch.from_numpy(z["x_r"][b:e]).to(device)])
+    loss = torch.zeros(1, device=device)
+    xg = torch.empty_like(panel) if input_grad else None
+    out, _ = step.run(panel, torch.from_numpy(z["target"][b:e]).to(device), loss, train=True, input_grad=xg)
+    return out, loss, {k: p.grad for k, p in m.named_parameters()}, xg, m.batch_norm.running_var, (b, e)
+
+
+def test_phase_api_world1_is_bit_identical():
+    dev = torch.device("cuda", 0)
+    os.environ["CGCN_NO_SIDE_STREAM"] = "1"      # same stream order in both runs (fixed-order reductions either way)
+    ref = _single_gpu_reference(dev)
+    got = _partitioned(dev, 0, 1)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    for k in ref[2]:
+        assert torch.equal(got[2][k], ref[2][k]), k
+    assert torch.equal(got[3], ref[3]) and torch.equal(got[4], ref[4])
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        ref = _single_gpu_reference(dev)
+        out, loss, grads, xg, rv, (b, e) = _partitioned(dev, rank, world)
+        errs = {"out": ogcn.max_rel(out.cpu(), ref[0][b:e].cpu()), "loss": abs(loss.item() - ref[1].item()) / abs(ref[1].item()),
+                "xgrad": ogcn.max_rel(xg.cpu(), ref[3][b:e].cpu()), "running_var": ogcn.max_rel(rv.cpu(), ref[4].cpu())}
+        for k in ref[2]:
+            errs["grad." + k] = ogcn.max_rel(grads[k].cpu(), ref[2][k].cpu())
+        ret[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_row_partition_two_gpus_matches_single_gpu():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        for k, v in ret[r].items():
+            assert v <= (1e-5 if not k.startswith("grad.") else 2e-5), (r, k, v)
