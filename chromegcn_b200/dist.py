@@ -112,8 +112,11 @@ def allgather_panel(local: torch.Tensor, parts: Sequence[Tuple[int, int]], out: 
     if world == 1:
         out.copy_(local)
         return out
-    # blocks may differ by one row: gather fixed-size padded blocks, then drop the padding
     rows_max = max(e - b for b, e in parts)
+    if all(e - b == rows_max for b, e in parts) and out.is_contiguous():
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)     # equal blocks: gather in place
+        return out
+    # blocks differ by one row: gather fixed-size padded blocks, then drop the padding
     rank = dist.get_rank(group)
     b0, e0 = parts[rank]
     send = torch.zeros(rows_max, width, dtype=local.dtype, device=local.device)
