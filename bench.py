@@ -187,7 +187,8 @@ def main():
     # ---- synthetic inputs; adjacency built by the product path (cgcn_adj_build) for this rank's chromosomes
     sizes = {c: synthetic.num_windows(c) for c in chroms}
     costs = {c: cdist.chromosome_cost(sizes[c], HIC_EDGES + sizes[c]) for c in chroms}
-    shards = cdist.lpt_shards(costs, world)
+    schedule = cdist.balanced_schedule(costs, world)
+    shards = cdist.schedule_shards(schedule, world)
     mine = shards[rank]
     graphs, feats_host, panels, targets, probs = {}, {}, {}, {}, {}
     local_edges = 0
@@ -216,10 +217,10 @@ def main():
             dist.broadcast(p.data, 0)
     engine = ChromosomeEngine(model, 2)
     optimizer = FlatSGD(model, lr=LR)
-    losses = torch.zeros(max(cdist.num_rounds(shards), 1), device=dev)
+    losses = torch.zeros(max(len(mine), 1), device=dev)
 
     def one_step():
-        cdist.sharded_train_epoch(engine, optimizer, shards, rank, graphs, panels, targets, probs, losses)
+        cdist.sharded_train_epoch(engine, optimizer, schedule, rank, graphs, panels, targets, probs, losses)
 
     def barrier():
         if world > 1:
@@ -338,7 +339,9 @@ def main():
                 "config": {"workload": workload_name(args.workload), "d_model": D, "gcn_layers": LAYERS, "nclass": NCLASS,
                            "gate": True, "adj_type": "hic", "hicnorm": "SQRTVC", "hicsize": HIC_EDGES, "optim": "sgd",
                            "gcn_dropout": DROPOUT, "strands": 2, "total_stored_entries": total_edges,
-                           "parallelism": "chromosome-sharded x%d (LPT), flat-gradient allreduce per round" % world,
+                           "parallelism": "chromosome-sharded x%d, %d lock-step rounds per pass (balanced packing, gradient "
+                                          "accumulation inside a rank's cell), one flat-gradient allreduce + optimiser step per "
+                                          "round" % (world, len(schedule)),
                            "l2": "inputs larger than L2 (126 MB): %.2f GB of resident feature panels + targets cycled per "
                                  "step, ~50 panel-sized passes per chromosome" % (
                                      sum(sizes[c] for c in chroms) * (2 * D * 4 + NCLASS * 4) / 1e9),

@@ -229,12 +229,32 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
   const uint32_t s_tmem_ptr = bar_tempty + 16;
   const uint32_t sBias = sBar + 256;                            // 128 floats (zero padded): the L1 is all shared memory here
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));        // generic pointer to the aligned base
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles = (p.m + TILE - 1) / TILE;
+
   if (threadIdx.x < TILE)
     reinterpret_cast<float*>(gen + (sBias - base))[threadIdx.x] =
         (p.bias != nullptr && static_cast<int>(threadIdx.x) < p.n_valid) ? __ldg(p.bias + threadIdx.x) : 0.f;
+
+  // Producers put their first tile's loads in flight before anything else: the B image copy, barrier init and
+  // TMEM allocation below then overlap with the DRAM latency of the first A tile.
+  const int pt = static_cast<int>(threadIdx.x) - (MMA_WARP + 1) * 32;      // 0..255 for producer threads
+  float4 v[4][4];      // register ring: one whole tile (4 k-chunks x 4 float4) of look-ahead = 64 KB in flight per SM
+  auto issue = [&](int64_t tile, int kc) {
+    const int64_t row0 = tile * TILE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = pt + PROD_THREADS * i;
+      const int r = u >> 3, c = u & 7;
+      const int64_t grow = row0 + r;
+      const int col = kc * KCH + c * 4;
+      v[kc][i] = (tile < tiles && grow < p.m && col < p.k_valid) ? ldg4(p.A + grow * p.lda + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (warp > MMA_WARP) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) issue(blockIdx.x, kc);
+  }
 
   // B image: global -> smem (already swizzled), all threads
   {
@@ -274,23 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
 
   if (warp > MMA_WARP) {
     // ===================== producers =====================
-    const int pt = threadIdx.x - (MMA_WARP + 1) * 32;           // 0..255
     uint32_t stage = 0, phase = 0;
-    // register ring: one whole tile (4 k-chunks x 4 float4) of look-ahead per thread = 64 KB in flight per SM
-    float4 v[4][4];
-    auto issue = [&](int64_t tile, int kc) {
-      const int64_t row0 = tile * TILE;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int u = pt + PROD_THREADS * i;
-        const int r = u >> 3, c = u & 7;
-        const int64_t grow = row0 + r;
-        const int col = kc * KCH + c * 4;
-        v[kc][i] = (tile < tiles && grow < p.m && col < p.k_valid) ? ldg4(p.A + grow * p.lda + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-#pragma unroll
-    for (int kc = 0; kc < 4; ++kc) issue(blockIdx.x, kc);
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {

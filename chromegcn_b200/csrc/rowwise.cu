@@ -329,7 +329,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, 
 // ------------------------------------------------------------------------------ gate backward
 
 template <int DV, int S, int HEAD>
-__global__ void __launch_bounds__(RW_THREADS) gate_bwd_kernel(const GateBwdArgs a) {
+__global__ void __launch_bounds__(RW_THREADS, (DV == 1) ? 3 : 1) gate_bwd_kernel(const GateBwdArgs a) {
   constexpr int D = DV * 128;
   constexpr int K = 2 * D + 4;
   extern __shared__ __align__(16) float red[];

@@ -54,21 +54,91 @@ def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> None:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
 
 
-def sharded_train_epoch(engine, optimizer, shards: Sequence[Sequence[str]], rank: int, graphs, panels, targets,
+def default_rounds(n_items: int, world: int) -> int:
+    """Optimiser steps per pass over the chromosomes: one per chromosome on one rank (the reference,
+    finetune.py:39-49); `n_items // world` on several (each step then consumes about `world` chromosomes)."""
+    return n_items if world <= 1 else max(1, n_items // world)
+
+
+def balanced_schedule(costs: Dict[str, float], world: int, rounds: int = None) -> List[List[List[str]]]:
+    """`schedule[round][rank]` = chromosomes that rank processes (accumulating gradients) before the round's
+    all-reduce + optimiser step.  Rounds are lock-step, so the pass costs sum_r max_rank load(r, rank); with one
+    chromosome per cell that is 97 + 57 + 35 (k windows) on 8 ranks for the whole genome, 78 % efficient,
+    because chr1 alone sets the first round's pace.  Packing small chromosomes next to it does better: each
+    round gets a capacity (its largest item, or the even share of what is left) and is filled LPT-fashion;
+    the last round takes the remainder.  Deterministic."""
+    if rounds is None:
+        rounds = default_rounds(len(costs), world)
+    rounds = max(1, min(rounds, len(costs)))
+    if world <= 1:
+        order = sorted(costs, key=lambda k: (-costs[k], k))
+        return [[[c]] for c in order] if rounds == len(order) else [[list(order[r::rounds])] for r in range(rounds)]
+    remaining = sorted(costs, key=lambda k: (-costs[k], k))
+    schedule: List[List[List[str]]] = []
+    for r in range(rounds):
+        cells: List[List[str]] = [[] for _ in range(world)]
+        load = [0.0] * world
+        later_rounds = rounds - r - 1
+        if later_rounds == 0:                                   # last round: plain LPT of everything left
+            for c in remaining:
+                k = min(range(world), key=lambda i: (load[i], i))
+                cells[k].append(c)
+                load[k] += costs[c]
+            remaining = []
+        elif remaining:
+            cap = max(costs[remaining[0]], sum(costs[c] for c in remaining) / (world * (later_rounds + 1)))
+            kept: List[str] = []
+            for idx, c in enumerate(remaining):
+                k = min(range(world), key=lambda i: (load[i], i))
+                still_available = (len(remaining) - idx - 1) + len(kept)
+                if load[k] + costs[c] <= cap * 1.0001 and still_available >= later_rounds:
+                    cells[k].append(c)
+                    load[k] += costs[c]
+                else:
+                    kept.append(c)
+            remaining = kept
+        schedule.append(cells)
+    return schedule
+
+
+def schedule_cost(schedule: Sequence[Sequence[Sequence[str]]], costs: Dict[str, float]) -> float:
+    return sum(max(sum(costs[c] for c in cell) for cell in rnd) for rnd in schedule)
+
+
+def schedule_shards(schedule: Sequence[Sequence[Sequence[str]]], world: int) -> List[List[str]]:
+    return [[c for rnd in schedule for c in rnd[r]] for r in range(world)]
+
+
+def sharded_train_epoch(engine, optimizer, schedule, rank: int, graphs, panels, targets,
                         probs: Dict[str, torch.Tensor], losses: torch.Tensor, group=None) -> None:
-    """One pass over all chromosomes on `len(shards)` ranks.  `graphs/panels/targets/probs` hold this
-    rank's chromosomes (device resident).  `losses[t]` receives the loss of this rank's t-th chromosome."""
+    """One pass over all chromosomes.  `schedule` comes from `balanced_schedule` (or is a plain list of
+    per-rank lists = one chromosome per rank per round, `lpt_shards`).  `graphs/panels/targets/probs` hold this
+    rank's chromosomes (device resident).  `losses[i]` receives the loss of this rank's i-th chromosome.
+    Every round ends with ONE all-reduce of the flat gradient buffer and the same optimiser step on every rank,
+    on the mean gradient of the round's chromosomes."""
     from .engine import flat_params
-    mine = shards[rank]
     fp = flat_params(engine.model)
-    for t in range(num_rounds(shards)):
-        if t < len(mine):
-            c = mine[t]
-            engine.run(graphs[c], panels[c], targets[c], probs[c], losses[t: t + 1], train=True)
-        else:
+    if schedule and isinstance(schedule[0], (list, tuple)) and (not schedule[0] or isinstance(schedule[0][0], str)):
+        shards = schedule                                        # per-rank lists: lock-step, one chromosome per cell
+        schedule = [[[s[t]] if t < len(s) else [] for s in shards] for t in range(num_rounds(shards))]
+    acc = None
+    i = 0
+    for rnd in schedule:
+        mine = rnd[rank]
+        if len(mine) == 0:
             fp.flat_grad.zero_()
+        for j, c in enumerate(mine):
+            engine.run(graphs[c], panels[c], targets[c], probs[c], losses[i: i + 1], train=True)
+            i += 1
+            if len(mine) > 1:                                    # accumulate over the cell (backward overwrites)
+                if j == 0:
+                    acc = fp.flat_grad.clone() if acc is None else acc.copy_(fp.flat_grad)
+                else:
+                    acc.add_(fp.flat_grad)
+        if len(mine) > 1:
+            fp.flat_grad.copy_(acc)
         allreduce_gradients(fp.flat_grad, group)
-        optimizer.grad_scale = 1.0 / max(active_in_round(shards, t), 1)
+        optimizer.grad_scale = 1.0 / max(sum(len(cell) for cell in rnd), 1)
         optimizer.step()
 
 

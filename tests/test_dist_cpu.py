@@ -35,6 +35,25 @@ def test_lpt_shards_cover_and_balance():
     assert sum(cdist.active_in_round(s8, t) for t in range(cdist.num_rounds(s8))) == len(chroms)
 
 
+def test_balanced_schedule_properties():
+    chroms = synthetic.WHOLE_GENOME
+    costs = {c: cdist.chromosome_cost(synthetic.num_windows(c), 500000 + synthetic.num_windows(c)) for c in chroms}
+    total = sum(costs.values())
+    for world in (1, 2, 4, 8):
+        sch = cdist.balanced_schedule(costs, world)
+        assert len(sch) == cdist.default_rounds(len(chroms), world)
+        assert all(len(r) == world for r in sch)
+        assert all(any(len(cell) for cell in r) for r in sch)                         # no empty round
+        assert sorted(c for r in sch for cell in r for c in cell) == sorted(chroms)   # every chromosome exactly once
+        eff = total / world / cdist.schedule_cost(sch, costs)
+        assert eff >= {1: 0.999, 2: 0.95, 4: 0.90, 8: 0.87}[world], (world, eff)
+        assert cdist.balanced_schedule(costs, world) == sch                           # deterministic
+        shards = cdist.schedule_shards(sch, world)
+        assert sorted(sum(shards, [])) == sorted(chroms)
+    one = cdist.balanced_schedule(costs, 1)
+    assert [len(r[0]) for r in one] == [1] * 23                                        # one step per chromosome on one rank
+
+
 def test_row_partition_and_local_csr():
     n = 1003
     parts = cdist.row_partition(n, 8)
