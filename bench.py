@@ -39,7 +39,7 @@ CPU_SAMPLE = ["chr19", "chr20", "chr21", "chr22"]
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="wg", choices=["wg", "c1"])
@@ -116,6 +116,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def start(self):
         try:
@@ -128,7 +135,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -138,8 +145,18 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        # nvidia-smi needs ~1 s to come up, so it is started before the data is built and its rows are
+        # time-stamped: the reported samples are the ones that fall inside the timed region (plus one
+        # sampling period of slack either side, the loop period being 20 ms).
+        rows = self.rows
+        window = "timed region"
+        if self.t0 is not None and self.t1 is not None:
+            rows = [(t, r) for t, r in self.rows if self.t0 - 0.02 <= t <= self.t1 + 0.02]
+            if not rows:      # region shorter than one sampling period: fall back to the warm-up + timed load window
+                rows = [(t, r) for t, r in self.rows if self.load0 - 0.02 <= t <= self.t1 + 0.02]
+                window = "warm-up + timed region (timed region shorter than one 20 ms sample)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for _, r in rows:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 6:
                 continue
@@ -153,7 +170,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------- GPU arm
@@ -180,6 +197,9 @@ def main():
     _lib.require_cuda()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # started here so that nvidia-smi is already looping when the timed region begins
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -227,15 +247,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler.load0 = time.monotonic()
     for _ in range(warmup):
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record()
     torch.cuda.nvtx.range_push("timed")
     for _ in range(steps):
@@ -243,6 +262,7 @@ def main():
     torch.cuda.nvtx.range_pop()
     ev1.record()
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
