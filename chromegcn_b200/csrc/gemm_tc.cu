@@ -67,6 +67,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy (no tensor map): contiguous global -> shared, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -202,6 +211,7 @@ struct RowPanelTcArgs {
   float* C;
   int64_t ldc;
   int64_t m;
+  int64_t rows_per_cta;        // each CTA owns one contiguous row range (its last tile may be partial)
   const int32_t* rowscale_rowptr;
   const float* rowscale_inv;
   int rowscale_group;
@@ -226,11 +236,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
   const uint32_t sStg = sA + RP_STAGES * RP_STAGE_BYTES;        // epilogue staging, 4 warps x 4.5 KB
   const uint32_t sBar = sStg + STG_BYTES;                       // full[S] empty[S] tfull[2] tempty[2] | tmem ptr
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * RP_STAGES, bar_tfull = sBar + 16 * RP_STAGES, bar_tempty = bar_tfull + 16;
-  const uint32_t s_tmem_ptr = bar_tempty + 16;
+  const uint32_t s_tmem_ptr = bar_tempty + 16, bar_b = bar_tempty + 24;
   const uint32_t sBias = sBar + 256;                            // 128 floats (zero padded): the L1 is all shared memory here
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));        // generic pointer to the aligned base
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t tiles = (p.m + TILE - 1) / TILE;
+  // Contiguous, equally sized row range per CTA instead of round-robin whole tiles: the kernel is bound by
+  // the bytes it moves, and a partial last tile moves only its valid rows, so every SM carries the same
+  // traffic (m / grid rows) even when m / 128 is not a multiple of the grid.
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.x) * p.rows_per_cta;
+  const int64_t r_end = r_begin + p.rows_per_cta < p.m ? r_begin + p.rows_per_cta : p.m;
+  const int ntile = r_end > r_begin ? static_cast<int>((r_end - r_begin + TILE - 1) / TILE) : 0;
 
   if (threadIdx.x < TILE)
     reinterpret_cast<float*>(gen + (sBias - base))[threadIdx.x] =
@@ -240,40 +255,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
   // TMEM allocation below then overlap with the DRAM latency of the first A tile.
   const int pt = static_cast<int>(threadIdx.x) - (MMA_WARP + 1) * 32;      // 0..255 for producer threads
   float4 v[4][4];      // register ring: one whole tile (4 k-chunks x 4 float4) of look-ahead = 64 KB in flight per SM
-  auto issue = [&](int64_t tile, int kc) {
-    const int64_t row0 = tile * TILE;
+  auto issue = [&](int t, int kc) {
+    const int64_t row0 = r_begin + static_cast<int64_t>(t) * TILE;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int u = pt + PROD_THREADS * i;
       const int r = u >> 3, c = u & 7;
       const int64_t grow = row0 + r;
       const int col = kc * KCH + c * 4;
-      v[kc][i] = (tile < tiles && grow < p.m && col < p.k_valid) ? ldg4(p.A + grow * p.lda + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[kc][i] = (grow < r_end && col < p.k_valid) ? ldg4(p.A + grow * p.lda + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   if (warp > MMA_WARP) {
 #pragma unroll
-    for (int kc = 0; kc < 4; ++kc) issue(blockIdx.x, kc);
+    for (int kc = 0; kc < 4; ++kc) issue(0, kc);
   }
 
-  // B image: global -> smem (already swizzled), all threads
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.b_img);
-    constexpr int N16 = RP_B_BYTES / 16;                        // 8192 x 16 B, batches of 8 loads in flight
-    for (int i0 = threadIdx.x; i0 < N16; i0 += THREADS * 8) {
-      uint4 t[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = i0 + j * THREADS;
-        t[j] = i < N16 ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = i0 + j * THREADS;
-        if (i < N16) sts128(sB + i * 16, t[j]);
-      }
-    }
-  }
+  // Barriers, then the B image (already swizzled by tc_prep_b_kernel) as 8 x 16 KB bulk copies that complete on
+  // bar_b: nothing but the first MMA waits for them.
   if (threadIdx.x == 0) {
     for (int s = 0; s < RP_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, NUM_PROD_WARPS);
@@ -283,7 +282,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, NUM_EPI_WARPS);
     }
+    mbar_init(bar_b, 1);
     fence_barrier_init();
+    mbar_expect_tx(bar_b, RP_B_BYTES);
+#pragma unroll 1
+    for (int i = 0; i < RP_B_BYTES / CHUNK_BYTES; ++i)
+      bulk_g2s(sB + i * CHUNK_BYTES, reinterpret_cast<const uint8_t*>(p.b_img) + i * CHUNK_BYTES, CHUNK_BYTES, bar_b);
   }
   if (warp == MMA_WARP) tmem_alloc(s_tmem_ptr, 256);
   fence_async_smem();
@@ -295,11 +299,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
   if (warp > MMA_WARP) {
     // ===================== producers =====================
     uint32_t stage = 0, phase = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int t = 0; t < ntile; ++t) {
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        if (warp == MMA_WARP + 1) TC_TRACE(0, static_cast<int>((tile - blockIdx.x) / gridDim.x) * 4 + kc);
+        if (warp == MMA_WARP + 1) TC_TRACE(0, t * 4 + kc);
         const uint32_t sHi = sA + stage * RP_STAGE_BYTES, sLo = sHi + CHUNK_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -311,12 +315,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
           sts128(sHi + off, hi);
           sts128(sLo + off, lo);
         }
-        if (warp == MMA_WARP + 1) TC_TRACE(1, static_cast<int>((tile - blockIdx.x) / gridDim.x) * 4 + kc);
+        if (warp == MMA_WARP + 1) TC_TRACE(1, t * 4 + kc);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-        if (warp == MMA_WARP + 1) TC_TRACE(2, static_cast<int>((tile - blockIdx.x) / gridDim.x) * 4 + kc);
-        issue(tile + gridDim.x, kc);                            // refill this slot for the next tile
+        if (warp == MMA_WARP + 1) TC_TRACE(2, t * 4 + kc);
+        if (t + 1 < ntile) issue(t + 1, kc);                    // refill this slot for the next tile
         if (++stage == RP_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -326,8 +330,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(false, false);
-    uint32_t stage = 0, phase = 0, it = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    uint32_t stage = 0, phase = 0;
+    if (ntile > 0) mbar_wait(bar_b, 0);                         // weights image landed
+    for (uint32_t it = 0; it < static_cast<uint32_t>(ntile); ++it) {
       const uint32_t acc = it & 1;
       mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -360,14 +365,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
     }
   } else {
     // ===================== epilogue =====================
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0; it < static_cast<uint32_t>(ntile); ++it) {
       const uint32_t acc = it & 1;
       mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
-      const int64_t grow = tile * TILE + warp * 32 + lane;
+      const int64_t tile_row0 = r_begin + static_cast<int64_t>(it) * TILE;
+      const int64_t grow = tile_row0 + warp * 32 + lane;
       float scale = 1.0f;
-      if ((p.rowscale_rowptr != nullptr || p.rowscale_inv != nullptr) && grow < p.m)
+      if ((p.rowscale_rowptr != nullptr || p.rowscale_inv != nullptr) && grow < r_end)
         scale = row_scale(p.rowscale_rowptr, p.rowscale_inv, static_cast<int>(grow / p.rowscale_group));
       const uint32_t stg = sStg + warp * (32 * STG_PITCH * 4);
       const int n_store = (p.n_valid + 3) & ~3;
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
           o[j] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
         }
         if (warp == 0) TC_TRACE(6, static_cast<int>(it) * 8 + cc * 2);
-        store_block_coalesced(stg, o, lane, p.C, p.ldc, tile * TILE + warp * 32, p.m, cc * 32, n_store);
+        store_block_coalesced(stg, o, lane, p.C, p.ldc, tile_row0 + warp * 32, r_end, cc * 32, n_store);
         if (warp == 0) TC_TRACE(6, static_cast<int>(it) * 8 + cc * 2 + 1);
       }
       tc_fence_before();
@@ -591,9 +596,11 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
   uint32_t* img = static_cast<uint32_t*>(workspace);
   tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, n, k, img);
   CGCN_TRY(check_launch("tc_prep_b_kernel"));
-  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rowscale_rowptr, rowscale_inv, rowscale_group, n, k, nullptr};
   const int64_t tiles = (m + tc::TILE - 1) / tc::TILE;
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  const int64_t rows_per_cta = ((m + grid - 1) / grid + 7) / 8 * 8;
+  grid = static_cast<int>((m + rows_per_cta - 1) / rows_per_cta);
+  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rows_per_cta, rowscale_rowptr, rowscale_inv, rowscale_group, n, k, nullptr};
   static const bool trace = getenv("CGCN_TC_TRACE") != nullptr;
   if (trace) {                                                  // developer aid: synchronous, prints CTA 0's timeline
     long long* d = nullptr;

@@ -23,7 +23,7 @@ def timeit(fn, reps=20):
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "rowpanel"):
-    for m in (128, 1000, 40000, 194330):
+    for m in (128, 1000, 40000, 102000, 194330, 400000):
         for bt in (False, True):
             a = torch.randn(m, 128, device=dev)
             w = torch.randn(128, 128, device=dev) * 0.1
@@ -39,7 +39,7 @@ if which in ("all", "rowpanel"):
             print("rowpanel m=%6d bt=%d  tc err %.2e (%.1f us)   ffma err %.2e (%.1f us)   GB/s tc %.0f" %
                   (m, bt, e2, t2, e1, t1, 2 * m * 512 / t2 / 1e3), flush=True)
 if which in ("all", "gram"):
-    for m in (32, 1000, 40000, 194330):
+    for m in (32, 1000, 40000, 102000, 194330, 400000):
         a = torch.randn(m, 128, device=dev)
         b = torch.randn(m, 128, device=dev)
         want = a.double().t() @ b.double()
