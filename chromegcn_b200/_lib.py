@@ -11,7 +11,8 @@ from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libchromegcn.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
+MAX_LAYERS = 4
 
 
 class ChromeGCNNativeError(RuntimeError):
@@ -24,8 +25,8 @@ class Graph(C.Structure):
 
 
 class Params(C.Structure):
-    _fields_ = [("gc_w", C.c_void_p * 2), ("gc_b", C.c_void_p * 2), ("gate_w", C.c_void_p * 2),
-                ("gate_b", C.c_void_p * 2), ("bn_w", C.c_void_p), ("bn_b", C.c_void_p),
+    _fields_ = [("gc_w", C.c_void_p * MAX_LAYERS), ("gc_b", C.c_void_p * MAX_LAYERS), ("gate_w", C.c_void_p * MAX_LAYERS),
+                ("gate_b", C.c_void_p * MAX_LAYERS), ("bn_w", C.c_void_p), ("bn_b", C.c_void_p),
                 ("out_w", C.c_void_p), ("out_b", C.c_void_p)]
 
 
@@ -35,10 +36,11 @@ class Model(C.Structure):
                 ("training", C.c_int32), ("gemm_impl", C.c_int32), ("need_input_grad", C.c_int32),
                 ("out_ld", C.c_int32),
                 ("dropout_p", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("row_begin", C.c_int32),
+                ("gate_off", C.c_int32), ("reserved0", C.c_int32),
                 ("seed", C.c_uint64), ("step", C.c_uint64),
                 ("params", Params), ("grads", Params),
                 ("bn_running_mean", C.c_void_p), ("bn_running_var", C.c_void_p), ("bn_num_batches_tracked", C.c_void_p),
-                ("x_in", C.c_void_p), ("x_in_grad", C.c_void_p), ("out", C.c_void_p), ("gate", C.c_void_p * 2),
+                ("x_in", C.c_void_p), ("x_in_grad", C.c_void_p), ("out", C.c_void_p), ("gate", C.c_void_p * MAX_LAYERS),
                 ("out_grad", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("stream", C.c_void_p),
                 ("n_total", C.c_int64), ("x_full", C.c_void_p), ("bn_sums", C.c_void_p)]

@@ -21,6 +21,15 @@ from .graph import HiCGraph
 
 PARAM_ORDER = ["GC1.weight", "GC1.bias", "W1.weight", "W1.bias", "GC2.weight", "GC2.bias", "W2.weight", "W2.bias",
                "batch_norm.weight", "batch_norm.bias", "out.weight", "out.bias"]
+MAX_LAYERS = _lib.MAX_LAYERS
+
+
+def param_order(layers: int) -> List[str]:
+    """State-dict names in the reference's order for an `layers`-layer model (GC3/W3... only in extended mode)."""
+    names: List[str] = []
+    for l in range(1, layers + 1):
+        names += ["GC%d.weight" % l, "GC%d.bias" % l, "W%d.weight" % l, "W%d.bias" % l]
+    return names + ["batch_norm.weight", "batch_norm.bias", "out.weight", "out.bias"]
 
 
 def padded_classes(nclass: int) -> int:
@@ -130,9 +139,11 @@ def build_model_struct(graph: HiCGraph, d: int, nclass: int, layers: int, strand
                        running_mean: torch.Tensor, running_var: torch.Tensor, num_batches: Optional[torch.Tensor],
                        x_in: torch.Tensor, x_in_grad: Optional[torch.Tensor], out: torch.Tensor,
                        gates: List[Optional[torch.Tensor]], out_grad: Optional[torch.Tensor], workspace: torch.Tensor,
-                       gemm_impl: int = 0, bn_momentum: float = 0.1, bn_eps: float = 1e-5, out_ld: int = 0) -> _lib.Model:
+                       gemm_impl: int = 0, bn_momentum: float = 0.1, bn_eps: float = 1e-5, out_ld: int = 0,
+                       gate_off: bool = False) -> _lib.Model:
     m = _lib.Model()
     m.out_ld = out_ld
+    m.gate_off = 1 if gate_off else 0
     m.graph = graph.c_struct()
     m.d, m.nclass, m.layers, m.strands = d, nclass, layers, strands
     m.training = 1 if training else 0
@@ -146,8 +157,8 @@ def build_model_struct(graph: HiCGraph, d: int, nclass: int, layers: int, strand
     m.bn_running_mean, m.bn_running_var = _lib.ptr(running_mean), _lib.ptr(running_var)
     m.bn_num_batches_tracked = _lib.ptr(num_batches)
     m.x_in, m.x_in_grad, m.out = _lib.ptr(x_in), _lib.ptr(x_in_grad), _lib.ptr(out)
-    m.gate[0] = _lib.ptr(gates[0])
-    m.gate[1] = _lib.ptr(gates[1]) if len(gates) > 1 and gates[1] is not None else None
+    for l in range(layers):
+        m.gate[l] = _lib.ptr(gates[l])
     m.out_grad = _lib.ptr(out_grad)
     m.workspace, m.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     m.stream = _lib.current_stream()
@@ -180,7 +191,8 @@ class _ChromeGCNFn(torch.autograd.Function):
             bn = module.batch_norm
             m = build_model_struct(graph, d, nclass, layers, 1, training, module.dropout, seed, step, params, None,
                                    bn.running_mean, bn.running_var, bn.num_batches_tracked, x, None, out, gates, None, ws,
-                                   module.gemm_impl, bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld)
+                                   module.gemm_impl, bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld,
+                                   module.gate_off)
             _lib.check(lib.cgcn_model_forward(C.byref(m)), "cgcn_model_forward")
         ctx.module, ctx.graph, ctx.names = module, graph, names
         ctx.cfg = (n, d, nclass, layers, training, seed, step)
@@ -208,25 +220,40 @@ class _ChromeGCNFn(torch.autograd.Function):
             bn = module.batch_norm
             m = build_model_struct(graph, d, nclass, layers, 1, training, module.dropout, seed, step, params, grads,
                                    bn.running_mean, bn.running_var, None, x, dx, out, gates, dout, ws, module.gemm_impl,
-                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld)
+                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld, module.gate_off)
             _lib.check(lib.cgcn_model_backward(C.byref(m)), "cgcn_model_backward")
         return (dx, None, None, *[grads[k] for k in names])
 
 
 class ChromeGCN(nn.Module):
     """models/ChromeModels.py:21-52.  `gate` is accepted and ignored and `layers != 2` gives one
-    layer, exactly like the reference."""
+    layer, exactly like the reference.
 
-    def __init__(self, nfeat, nhid, nclass, dropout, gate, layers):
+    `extended=True` (not in the reference; the variant sweep of BASELINE.json needs "gcn_layers 3" and "gate off",
+    which the reference cannot express) honours both arguments: `layers` in 1..4 builds GC1..GC{layers} / W1..W{layers}
+    with the same per-layer recipe (dropout between consecutive layers), and `gate=False` makes every layer
+    `x <- tanh(A_hat x W + b)` (g == 1; the W{l} parameters stay in the state_dict and receive zero gradients).
+    `forward` still returns `(x_in, out, (g, g2), None)`; further gates are in `self.last_gates`."""
+
+    def __init__(self, nfeat, nhid, nclass, dropout, gate, layers, extended: bool = False):
         super().__init__()
         if nfeat != nhid:
             raise ValueError("ChromeGCN needs nhid == nfeat (W1 = Linear(nfeat, 1) is applied to an nhid-wide tensor, "
                              "models/ChromeModels.py:24-25)")
+        self.extended = bool(extended)
+        self.gate_off = self.extended and not bool(gate)
+        if self.extended:
+            if not 1 <= int(layers) <= MAX_LAYERS:
+                raise ValueError("extended ChromeGCN supports 1..%d layers" % MAX_LAYERS)
+            n_layers = int(layers)
+        else:
+            n_layers = 2 if layers == 2 else 1
         self.GC1 = GraphConvolution(nfeat, nhid, bias=True, init="xavier")
         self.W1 = nn.Linear(nfeat, 1)
-        if layers == 2:
-            self.GC2 = GraphConvolution(nhid, nfeat, bias=True, init="xavier")
-            self.W2 = nn.Linear(nfeat, 1)
+        for l in range(2, n_layers + 1):
+            setattr(self, "GC%d" % l, GraphConvolution(nhid, nfeat, bias=True, init="xavier"))
+            setattr(self, "W%d" % l, nn.Linear(nfeat, 1))
+        self.last_gates: List[torch.Tensor] = []
         self.dropout = dropout
         self.batch_norm = nn.BatchNorm1d(nfeat)
         self.out = nn.Linear(nfeat, nclass)
@@ -238,10 +265,13 @@ class ChromeGCN(nn.Module):
     # -- helpers shared with the fused trainer
     @property
     def num_layers(self) -> int:
-        return 2 if hasattr(self, "GC2") else 1
+        n = 1
+        while n < MAX_LAYERS and hasattr(self, "GC%d" % (n + 1)):
+            n += 1
+        return n
 
     def _param_names(self) -> List[str]:
-        return [k for k in PARAM_ORDER if self.num_layers == 2 or not (k.startswith("GC2") or k.startswith("W2"))]
+        return param_order(self.num_layers)
 
     def _param_tensors(self) -> List[torch.Tensor]:
         sd = dict(self.named_parameters())
@@ -263,5 +293,6 @@ class ChromeGCN(nn.Module):
         graph = self.resolve_graph(adj)
         res = _ChromeGCNFn.apply(x_in, self, graph, *self._param_tensors())
         out, g = res[0], res[1]
-        g2 = res[2] if self.num_layers == 2 else None
+        g2 = res[2] if self.num_layers >= 2 else None
+        self.last_gates = list(res[1:])
         return x_in, out, (g, g2), None

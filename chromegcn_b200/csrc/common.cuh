@@ -48,6 +48,13 @@ inline int check_launch(const char* what) {
   } while (0)
 
 int sm_count();                       // cached, current device
+
+// one weight operand of a tcgen05 row-panel contraction, to be split (hi/lo TF32) and swizzled into `img`
+struct TcImageSpec {
+  const float* B;
+  int b_transposed, n, k;
+  void* img;
+};
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // bump allocator over a caller-provided workspace

@@ -202,6 +202,32 @@ __global__ void tc_prep_b_kernel(const float* __restrict__ B, int b_transposed, 
   img[(4 * CHUNK_BYTES >> 2) + off] = lo;
 }
 
+// All weight images one model pass needs, in ONE launch (blockIdx.y = image): the weights only change at the
+// optimiser step, so the forward (and the backward) pass prepares its images up front instead of once per
+// contraction on the critical path.
+constexpr int PREP_MAX = 8;
+struct PrepBatchArgs {
+  const float* B[PREP_MAX];
+  uint32_t* img[PREP_MAX];
+  int b_transposed[PREP_MAX], n_valid[PREP_MAX], k_valid[PREP_MAX];
+};
+__global__ void tc_prep_b_batch_kernel(const PrepBatchArgs a) {
+  const int w = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= TILE * TILE) return;
+  const int n = idx >> 7, k = idx & 127;
+  const int n_valid = a.n_valid[w], k_valid = a.k_valid[w];
+  const float* __restrict__ B = a.B[w];
+  float v = 0.f;
+  if (n < n_valid && k < k_valid) v = a.b_transposed[w] ? __ldg(B + n * k_valid + k) : __ldg(B + k * n_valid + n);
+  uint32_t hi, lo;
+  split_tf32(v, hi, lo);
+  const int kc = k >> 5, kk = k & 31;
+  const int off = (kc * CHUNK_BYTES + (n >> 3) * ATOM_BYTES + (n & 7) * 128 + (((kk >> 2) ^ (n & 7)) << 4) + (kk & 3) * 4) >> 2;
+  a.img[w][off] = hi;
+  a.img[w][(4 * CHUNK_BYTES >> 2) + off] = lo;
+}
+
 // ------------------------------------------------------------------ row-panel kernel
 struct RowPanelTcArgs {
   const float* A;
@@ -576,14 +602,33 @@ bool tc_gram_supported(int64_t lda, int64_t ldb, int ka, int nb, const void* A, 
 }
 size_t tc_workspace_bytes() { return tc::RP_B_BYTES + 256; }
 
+// Prepare up to 8 weight images with one launch.  specs[i].img: tc_workspace_bytes() bytes, 16-byte aligned.
+int tc_prep_images(const TcImageSpec* specs, int count, cudaStream_t stream) {
+  CGCN_REQUIRE(count >= 0 && count <= tc::PREP_MAX, "tc_prep_images: count=%d", count);
+  if (count == 0) return CGCN_OK;
+  tc::PrepBatchArgs a{};
+  for (int i = 0; i < count; ++i) {
+    CGCN_REQUIRE(specs[i].B && specs[i].img && aligned16(specs[i].img) && specs[i].n >= 1 && specs[i].n <= 128 && specs[i].k >= 1 &&
+                     specs[i].k <= 128,
+                 "tc_prep_images: bad spec %d", i);
+    a.B[i] = specs[i].B;
+    a.img[i] = static_cast<uint32_t*>(specs[i].img);
+    a.b_transposed[i] = specs[i].b_transposed;
+    a.n_valid[i] = specs[i].n;
+    a.k_valid[i] = specs[i].k;
+  }
+  tc::tc_prep_b_batch_kernel<<<dim3((tc::TILE * tc::TILE + 255) / 256, count), 256, 0, stream>>>(a);
+  return check_launch("tc_prep_b_batch_kernel");
+}
+
 int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                      int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
-                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     void* workspace, size_t workspace_bytes, const void* ready_image, cudaStream_t stream) {
   CGCN_REQUIRE(A && B && C, "cgcn_gemm_rowpanel: null operand");
   CGCN_REQUIRE(tc_rowpanel_supported(lda, ldc, n, k, A, C),
                "cgcn_gemm_rowpanel(tcgen05): needs n, k <= 128 and 16-byte aligned rows padded to a multiple of 4 floats");
   CGCN_REQUIRE(bias == nullptr || aligned16(bias), "cgcn_gemm_rowpanel(tcgen05): bias must be 16-byte aligned");
-  if (workspace == nullptr || workspace_bytes < tc_workspace_bytes() || !aligned16(workspace)) {
+  if (ready_image == nullptr && (workspace == nullptr || workspace_bytes < tc_workspace_bytes() || !aligned16(workspace))) {
     set_error("cgcn_gemm_rowpanel(tcgen05): needs a %zu-byte, 16-byte aligned workspace", tc_workspace_bytes());
     return CGCN_ERR_WORKSPACE;
   }
@@ -593,9 +638,13 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
     CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_rowpanel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::RP_SMEM));
     attr_set = true;
   }
-  uint32_t* img = static_cast<uint32_t*>(workspace);
-  tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, n, k, img);
-  CGCN_TRY(check_launch("tc_prep_b_kernel"));
+  const uint32_t* img = static_cast<const uint32_t*>(ready_image);      // prepared by tc_prep_images for this (B, n, k)
+  if (img == nullptr) {
+    uint32_t* fresh = static_cast<uint32_t*>(workspace);
+    tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, n, k, fresh);
+    CGCN_TRY(check_launch("tc_prep_b_kernel"));
+    img = fresh;
+  }
   const int64_t tiles = (m + tc::TILE - 1) / tc::TILE;
   int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   const int64_t rows_per_cta = ((m + grid - 1) / grid + 7) / 8 * 8;

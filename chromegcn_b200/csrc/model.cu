@@ -26,7 +26,8 @@ int gemm_gram_ffma(const float* A, int64_t lda, const float* B, int64_t ldb, flo
 size_t gram_workspace_bytes(int64_t m);
 int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                      int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
-                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                     void* workspace, size_t workspace_bytes, const void* ready_image, cudaStream_t stream);
+int tc_prep_images(const TcImageSpec* specs, int count, cudaStream_t stream);
 int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
                  int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 bool tc_rowpanel_supported(int64_t lda, int64_t ldc, int n, int k, const void* A, const void* C);
@@ -71,9 +72,10 @@ int sm_count() {
 static thread_local int tls_rp_ordinal = 0, tls_gr_ordinal = 0;   // developer aid (CGCN_TC_MASK_RP / _GR bitmasks)
 int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                            int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
-                           int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                           int impl, void* ws, size_t ws_bytes, cudaStream_t stream, const void* ready_image = nullptr) {
   static const char* dis = getenv("CGCN_TC_DISABLE");          // developer aid: "rowpanel", "gram" or "rowscale"
-  bool tc_ok = tc_rowpanel_supported(lda, ldc, n, k, A, C) && ws != nullptr && ws_bytes >= tc_workspace_bytes();
+  bool tc_ok = tc_rowpanel_supported(lda, ldc, n, k, A, C) &&
+               (ready_image != nullptr || (ws != nullptr && ws_bytes >= tc_workspace_bytes()));
   if (dis && (strstr(dis, "rowpanel") || (strstr(dis, "rowscale") && rowscale_rowptr) || (strstr(dis, "head") && (n != 128 || k != 128)))) tc_ok = false;
   static const char* mask_s = getenv("CGCN_TC_MASK_RP");
   if (mask_s && !((atoi(mask_s) >> tls_rp_ordinal) & 1)) tc_ok = false;
@@ -84,7 +86,7 @@ int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_tr
   }
   if (impl == 2 || (impl == 0 && tc_ok))
     return gemm_rowpanel_tc(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, ws, ws_bytes,
-                            stream);
+                            ready_image, stream);
   return gemm_rowpanel_ffma(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, stream);
 }
 
@@ -130,14 +132,17 @@ static int side_stream(SideStream** out) {
 }
 
 // ---- workspace layout (offsets in floats)
+constexpr int ML = CGCN_MAX_LAYERS;
 struct WsLayout {
-  size_t ax[2], z[2], xo[2], hb;
+  size_t ax[ML], z[ML], xo[ML], hb;
   size_t bn_mean, bn_rstd, bn_c1, bn_c2;
-  size_t dA, dB, dC, dD;
+  size_t dy[ML], dX, dY, dC;           // backward: one dy panel per layer (the side stream reads it until the join) + 3 rotating
   size_t partial, partial_floats;      // main-stream reductions (BatchNorm)
-  size_t partial_l[2], partial_side;   // per-layer gate-backward partials and the side stream's own (column sums)
+  size_t partial_l[ML], partial_side;  // per-layer gate-backward partials and the side stream's own (column sums)
   size_t gram, gram_bytes;
-  size_t tc, tc_bytes;
+  size_t tc, tc_bytes;                 // one tcgen05 weight image (hi/lo TF32, swizzled): 128 KB
+  size_t img_fwd[ML + 1];              // GC_l.weight (l < L), out.weight^T          -- prepared once per forward
+  size_t img_bwd[ML + 1];              // out.weight, GC_l.weight^T                  -- prepared once per backward
   size_t total_floats;
 };
 
@@ -152,7 +157,7 @@ static WsLayout make_layout(int n, int d, int nclass, int layers, int strands) {
     return r;
   };
   const size_t panel = static_cast<size_t>(n) * strands * d;
-  for (int l = 0; l < 2; ++l) {
+  for (int l = 0; l < ML; ++l) {
     const bool used = l < layers;
     L.ax[l] = take(used ? panel : 0);
     L.z[l] = take(used ? panel : 0);
@@ -163,22 +168,26 @@ static WsLayout make_layout(int n, int d, int nclass, int layers, int strands) {
   L.bn_rstd = take(static_cast<size_t>(strands) * d);
   L.bn_c1 = take(static_cast<size_t>(strands) * d);
   L.bn_c2 = take(static_cast<size_t>(strands) * d);
-  L.dA = take(panel);
-  L.dB = take(panel);
+  for (int l = 0; l < ML; ++l) L.dy[l] = take(l < layers ? panel : 0);
+  L.dX = take(panel);
+  L.dY = take(panel);
   L.dC = take(panel);
-  L.dD = take(panel);
   size_t per = static_cast<size_t>(2) * strands * d;
   if (per < static_cast<size_t>(2 * d + 4)) per = 2 * d + 4;
   if (per < 128) per = 128;
   L.partial_floats = static_cast<size_t>(rowwise_max_grid()) * per;
   L.partial = take(L.partial_floats);
-  L.partial_l[0] = take(L.partial_floats);
-  L.partial_l[1] = take(L.partial_floats);
+  for (int l = 0; l < ML; ++l) L.partial_l[l] = take(l < layers ? L.partial_floats : 0);
   L.partial_side = take(L.partial_floats);
   L.gram_bytes = gram_workspace_bytes(static_cast<int64_t>(n) * strands);
   L.gram = take((L.gram_bytes + 3) / 4);
   L.tc_bytes = tc_workspace_bytes();
   L.tc = take((L.tc_bytes + 3) / 4);
+  for (int i = 0; i <= ML; ++i) {
+    const bool used = i <= layers;
+    L.img_fwd[i] = take(used ? (L.tc_bytes + 3) / 4 : 0);
+    L.img_bwd[i] = take(used ? (L.tc_bytes + 3) / 4 : 0);
+  }
   L.total_floats = (off + 63) / 64 * 64;
   return L;
 }
@@ -189,11 +198,13 @@ static int validate(const cgcn_model* m, bool backward) {
   CGCN_REQUIRE((m->graph.vals == nullptr) == (m->graph.row_inv == nullptr), "cgcn_model: weighted graphs need vals and row_inv");
   CGCN_REQUIRE(m->d == 128, "cgcn_model: d=%d (the model path supports d = 128, the width main.py:62 fixes)", m->d);
   CGCN_REQUIRE(m->nclass >= 1 && m->nclass <= 128, "cgcn_model: nclass=%d must be in [1,128]", m->nclass);
-  CGCN_REQUIRE(m->layers == 1 || m->layers == 2, "cgcn_model: layers=%d", m->layers);
+  CGCN_REQUIRE(m->layers >= 1 && m->layers <= ML, "cgcn_model: layers=%d (1..%d)", m->layers, ML);
+  CGCN_REQUIRE(m->gate_off == 0 || m->gate_off == 1, "cgcn_model: gate_off=%d", m->gate_off);
   CGCN_REQUIRE(m->strands == 1 || m->strands == 2, "cgcn_model: strands=%d", m->strands);
   CGCN_REQUIRE(m->dropout_p >= 0.f && m->dropout_p < 1.f, "cgcn_model: dropout_p=%f", m->dropout_p);
   CGCN_REQUIRE(m->out_ld == 0 || m->out_ld >= m->nclass, "cgcn_model: out_ld=%d < nclass=%d", m->out_ld, m->nclass);
-  CGCN_REQUIRE(m->x_in && m->out && m->gate[0] && (m->layers == 1 || m->gate[1]), "cgcn_model: null activation pointer");
+  CGCN_REQUIRE(m->x_in && m->out, "cgcn_model: null activation pointer");
+  for (int l = 0; l < m->layers; ++l) CGCN_REQUIRE(m->gate[l] != nullptr, "cgcn_model: null gate[%d]", l);
   CGCN_REQUIRE(m->bn_running_mean && m->bn_running_var, "cgcn_model: null BatchNorm running statistics");
   for (int l = 0; l < m->layers; ++l)
     CGCN_REQUIRE(m->params.gc_w[l] && m->params.gc_b[l] && m->params.gate_w[l] && m->params.gate_b[l],
@@ -258,6 +269,35 @@ static Ctx make_ctx(const cgcn_model* m) {
   return c;
 }
 
+// dropout site ids (cgcn_dropout_mask): 0 = after layer 1, 1 = after BatchNorm, l + 1 = after layer l + 1 (l >= 1)
+static int layer_drop_site(int l) { return l == 0 ? 0 : l + 1; }
+
+// Weight images of the tcgen05 contractions, one launch per pass (the weights change only at the optimiser step).
+static bool use_images(const cgcn_model* m) {
+  static const bool off = getenv("CGCN_NO_IMAGES") != nullptr;      // developer aid: per-contraction preparation
+  return m->gemm_impl != 1 && !off;
+}
+static const void* fwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.ws + c.lay.img_fwd[i] : nullptr; }
+static const void* bwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.ws + c.lay.img_bwd[i] : nullptr; }
+
+static int prep_fwd_images(const Ctx& c) {
+  if (!use_images(c.m)) return CGCN_OK;
+  TcImageSpec sp[ML + 1];
+  int k = 0;
+  for (int l = 0; l < c.L; ++l) sp[k++] = TcImageSpec{c.m->params.gc_w[l], 0, c.d, c.d, c.ws + c.lay.img_fwd[l]};
+  sp[k++] = TcImageSpec{c.m->params.out_w, 1, c.C, c.d, c.ws + c.lay.img_fwd[c.L]};
+  return tc_prep_images(sp, k, c.st);
+}
+static int prep_bwd_images(const Ctx& c) {
+  if (!use_images(c.m)) return CGCN_OK;
+  TcImageSpec sp[ML + 1];
+  int k = 0;
+  sp[k++] = TcImageSpec{c.m->params.out_w, 0, c.d, c.C, c.ws + c.lay.img_bwd[0]};
+  for (int l = c.m->need_input_grad ? 0 : 1; l < c.L; ++l)
+    sp[k++] = TcImageSpec{c.m->params.gc_w[l], 1, c.d, c.d, c.ws + c.lay.img_bwd[1 + l]};
+  return tc_prep_images(sp, k, c.st);
+}
+
 // layer l: ax = A_hat x ; y = ax W + b ; gate.  `gather_src` is the panel the SpMM reads neighbours from (the
 // layer input itself on one GPU, the all-gathered copy of it when row-partitioned).
 static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
@@ -269,7 +309,7 @@ static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
   CGCN_TRY(spmm_launch(&m->graph, gather_src, ws + lay.ax[l], c.W, 1, nullptr, c.st));
   // y = ax W + b                                   (torch.mm + bias, models/SubLayers.py:43,50)
   CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.ax[l], c.d, m->params.gc_w[l], 0, m->params.gc_b[l], ws + lay.z[l], c.d, c.M, c.d,
-                                  c.d, nullptr, nullptr, 1, m->gemm_impl, c.tcws, lay.tc_bytes, c.st));
+                                  c.d, nullptr, nullptr, 1, m->gemm_impl, c.tcws, lay.tc_bytes, c.st, fwd_image(c, l)));
   // z = tanh(y); g = sigmoid(W z); x' = (1-g) x + g z; dropout between the layers
   //                                                (models/ChromeModels.py:38-42 / 44-46)
   GateFwdArgs a{};
@@ -282,8 +322,9 @@ static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
   a.xo = ws + lay.xo[l];
   a.stats_partial = ws + lay.partial;
   a.n = c.n;
+  a.gate_off = m->gate_off;
   const bool last = (l == c.L - 1);
-  a.drop = make_dropout(m->dropout_p, m->seed, m->step, 0, m->training && !last, c.drop_off);
+  a.drop = make_dropout(m->dropout_p, m->seed, m->step, layer_drop_site(l), m->training && !last, c.drop_off);
   int grid = 0;
   CGCN_TRY(gate_fwd_launch(a, c.d, c.S, last && m->training, &grid, c.st));
   if (last) {
@@ -322,7 +363,7 @@ static int fwd_head(const Ctx& c) {
   // out = hb Wout^T + bout                           (models/ChromeModels.py:51)
   const int ldo = m->out_ld > 0 ? m->out_ld : c.C;
   return gemm_rowpanel_dispatch(ws + lay.hb, c.d, m->params.out_w, 1, m->params.out_b, m->out, ldo, c.M, c.C, c.d, nullptr, nullptr,
-                                1, m->gemm_impl, c.tcws, lay.tc_bytes, c.st);
+                                1, m->gemm_impl, c.tcws, lay.tc_bytes, c.st, fwd_image(c, c.L));
 }
 
 static int model_forward(const cgcn_model* m) {
@@ -330,13 +371,15 @@ static int model_forward(const cgcn_model* m) {
   CGCN_TRY(validate(m, false));
   CGCN_REQUIRE(m->n_total <= 0, "cgcn_model_forward: row-partitioned graphs (n_total > 0) run through cgcn_model_phase");
   const Ctx c = make_ctx(m);
+  CGCN_TRY(prep_fwd_images(c));
   for (int l = 0; l < c.L; ++l) CGCN_TRY(fwd_layer(c, l, (l == 0) ? m->x_in : c.ws + c.lay.xo[l - 1]));
   return fwd_head(c);
 }
 
-// ---- backward stages.  Four scratch panels: `src` (gradient entering a gate stage), dy, dxd and the SpMM output;
-// dy is never written by the main stream while the side stream's gram kernel reads it.
-//   layer L-1: src = dA, dy = dB, dxd = dC, t -> dA, dx -> dD ;  layer L-2: src = dD, dy = dA, dxd = dC, t -> dD
+// ---- backward stages.  Scratch panels: one dy per layer (never rewritten while the side stream's gram kernel reads
+// it) and three rotating ones.  Layer l reads the gradient entering its gate stage from src(l), writes dy_l and
+// dxd (dC), overwrites src(l) with t_l = D^-1 (dy_l W_l^T), and the SpMM writes dx = dC + P t_l into the other
+// rotating panel, which is src(l-1).
 struct Fork {
   SideStream* side;
   cudaStream_t st, ss;
@@ -370,22 +413,26 @@ static int make_fork(const Ctx& c, Fork* f) {
   return CGCN_OK;
 }
 
+static float* bwd_src(const Ctx& c, int l) { return c.ws + ((((c.L - 1 - l) & 1) == 0) ? c.lay.dX : c.lay.dY); }
+static float* bwd_other(const Ctx& c, int l) { return c.ws + ((((c.L - 1 - l) & 1) == 0) ? c.lay.dY : c.lay.dX); }
+
 // head: side: d out.weight = dout^T hb ; d out.bias = colsum(dout).  main: d hb = dout Wout ; BatchNorm backward sums
 static int bwd_head(const Ctx& c, Fork& f) {
   const cgcn_model* m = c.m;
   const WsLayout& lay = c.lay;
   float* ws = c.ws;
-  float* dA = ws + lay.dA;
+  float* dhb = bwd_src(c, c.L - 1);
   void* gram_ws = ws + lay.gram;               // used by the side stream only
   const int ldo = m->out_ld > 0 ? m->out_ld : c.C;
+  CGCN_TRY(prep_bwd_images(c));
   CGCN_TRY(f.fork());
   CGCN_TRY(gemm_gram_dispatch(m->out_grad, ldo, ws + lay.hb, c.d, m->grads.out_w, c.d, c.M, c.C, c.d, 0, m->gemm_impl, gram_ws,
                               lay.gram_bytes, f.ss));
   CGCN_TRY(colsum_launch(m->out_grad, c.M, c.C, ldo, m->grads.out_b, ws + lay.partial_side, f.ss));
-  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, ldo, m->params.out_w, 0, nullptr, dA, c.d, c.M, c.d, c.C, nullptr, nullptr, 1,
-                                  m->gemm_impl, c.tcws, lay.tc_bytes, c.st));
+  CGCN_TRY(gemm_rowpanel_dispatch(m->out_grad, ldo, m->params.out_w, 0, nullptr, dhb, c.d, c.M, c.d, c.C, nullptr, nullptr, 1,
+                                  m->gemm_impl, c.tcws, lay.tc_bytes, c.st, bwd_image(c, 0)));
   BnBwdReduceArgs r{};
-  r.dhb = dA;
+  r.dhb = dhb;
   r.h = ws + lay.xo[c.L - 1];
   r.mean = ws + lay.bn_mean;
   r.rstd = ws + lay.bn_rstd;
@@ -399,12 +446,10 @@ static int bwd_head(const Ctx& c, Fork& f) {
                                 m->grads.bn_w, m->grads.bn_b, nullptr, c.dist ? m->bn_sums : nullptr, c.st);
 }
 
-static const float* bwd_src(const Ctx& c, int l) { return c.ws + ((l == c.L - 1) ? c.lay.dA : c.lay.dD); }
-static float* bwd_dy(const Ctx& c, int l) { return c.ws + ((l == c.L - 1) ? c.lay.dB : c.lay.dA); }
-
-// dx of layer l+1's input = dxd + P t, with t gathered from `t_gather` (layer l+1's t, or its all-gathered copy)
+// gradient entering layer l_from - 1 (or x_in_grad) = dxd + P t, with t gathered from `t_gather` (layer l_from's t, or
+// its all-gathered copy)
 static int bwd_propagate(const Ctx& c, int l_from, const float* t_gather) {
-  float* dx = (l_from == 0) ? c.m->x_in_grad : c.ws + c.lay.dD;
+  float* dx = (l_from == 0) ? c.m->x_in_grad : bwd_other(c, l_from);
   return spmm_launch(&c.m->graph, t_gather, dx, c.W, 0, c.ws + c.lay.dC, c.st);
 }
 
@@ -416,8 +461,8 @@ static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out) {
   float* ws = c.ws;
   const bool head = (l == c.L - 1);
   const bool need_dx = (l > 0) || m->need_input_grad;
-  const float* src = bwd_src(c, l);
-  float* dy = bwd_dy(c, l);
+  float* src = bwd_src(c, l);
+  float* dy = ws + lay.dy[l];
   *t_out = nullptr;
   if (head && c.dist)                // c1, c2 from the all-reduced BatchNorm backward sums
     CGCN_TRY(bn_bwd_finalize_launch(ws + lay.partial, 0, c.n_total, c.S, c.d, m->training, ws + lay.bn_c1, ws + lay.bn_c2, nullptr,
@@ -438,7 +483,7 @@ static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out) {
   a.dxd = need_dx ? ws + lay.dC : nullptr;
   a.partial = ws + lay.partial_l[l];
   a.n = c.n;
-  a.drop = make_dropout(m->dropout_p, m->seed, m->step, head ? 1 : 0, m->training, c.drop_off);
+  a.drop = make_dropout(m->dropout_p, m->seed, m->step, head ? 1 : layer_drop_site(l), m->training, c.drop_off);
   int grid = 0;
   CGCN_TRY(gate_bwd_launch(a, c.d, c.S, head, &grid, c.st));
   // side: bias / gate gradients from the partials, d W = (A_hat x)^T dy
@@ -448,10 +493,9 @@ static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out) {
                               lay.gram_bytes, f.ss));
   if (!need_dx) return CGCN_OK;
   // main: t = D^-1 (dy W^T) -> the panel that held `src`
-  float* t = const_cast<float*>(src);
-  CGCN_TRY(gemm_rowpanel_dispatch(dy, c.d, m->params.gc_w[l], 1, nullptr, t, c.d, c.M, c.d, c.d, m->graph.rowptr, m->graph.row_inv, c.S,
-                                  m->gemm_impl, c.tcws, lay.tc_bytes, c.st));
-  *t_out = t;
+  CGCN_TRY(gemm_rowpanel_dispatch(dy, c.d, m->params.gc_w[l], 1, nullptr, src, c.d, c.M, c.d, c.d, m->graph.rowptr, m->graph.row_inv, c.S,
+                                  m->gemm_impl, c.tcws, lay.tc_bytes, c.st, bwd_image(c, 1 + l)));
+  *t_out = src;
   return CGCN_OK;
 }
 
@@ -487,7 +531,10 @@ static int model_phase(const cgcn_model* m, int kind, int layer, const float** p
   const float* t = nullptr;
   switch (kind) {
     case CGCN_PHASE_FWD_LAYER:       // x_full holds the gathered input of `layer`
-      if (layer == 0) tls_rp_ordinal = tls_gr_ordinal = 0;
+      if (layer == 0) {
+        tls_rp_ordinal = tls_gr_ordinal = 0;
+        CGCN_TRY(prep_fwd_images(c));
+      }
       CGCN_TRY(fwd_layer(c, layer, m->x_full));
       if (publish && layer + 1 < c.L) *publish = c.ws + c.lay.xo[layer];
       return CGCN_OK;
@@ -540,7 +587,7 @@ extern "C" size_t cgcn_sizeof(int32_t which) {
 }
 
 extern "C" size_t cgcn_model_workspace_bytes(int32_t n, int32_t d, int32_t nclass, int32_t layers, int32_t strands) {
-  if (n < 1 || d < 1 || layers < 1 || layers > 2 || strands < 1 || strands > 2) return 0;
+  if (n < 1 || d < 1 || layers < 1 || layers > CGCN_MAX_LAYERS || strands < 1 || strands > 2) return 0;
   return make_layout(n, d, nclass, layers, strands).total_floats * sizeof(float);
 }
 

@@ -46,31 +46,64 @@ __device__ __forceinline__ void block_combine(float* red, int K, float* __restri
 }
 
 
-// Fixed-order parallel reduction of per-CTA partials: a CTA of (32 columns) x (FIN_SLICES slices of the
-// parts axis); every thread sums its slice in fp64, slices are combined in slice order in shared memory.
+// Fixed-order parallel reduction of per-CTA partials.  A CTA is (32 columns) x (FIN_SLICES slices of the parts
+// axis); a thread-block CLUSTER of gridDim.y CTAs (cluster dims 1 x gridDim.y x 1) shares one column block: slice
+// (cluster rank, threadIdx.y) sums parts q = rank*FIN_SLICES + y, stepping by gridDim.y*FIN_SLICES, in fp64; the
+// slices of a CTA are combined in slice order in its shared memory, and cluster rank 0 then reads the other CTAs'
+// sums through distributed shared memory in rank order.  One launch, >= 8x the CTAs of a single-CTA-per-column-
+// block reduction (these kernels sit on the critical path between two panel kernels), and still deterministic.
+// Every thread of every CTA must call this; the result is valid in threads with threadIdx.y == 0 of cluster rank 0
+// (`owner`).
 constexpr int FIN_SLICES = 32;
+constexpr int FIN_MAX_CLUSTER = 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local_smem_ptr, uint32_t cta_rank) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local_smem_ptr));
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta_rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
 
 template <int NV>
-__device__ __forceinline__ void reduce_parts(const float* __restrict__ partial, int parts, size_t stride,
+__device__ __forceinline__ bool reduce_parts(const float* __restrict__ partial, int parts, size_t stride,
                                              const int (&offs)[NV], bool active, double (&out)[NV]) {
   __shared__ double sh[FIN_SLICES][32][NV];
+  __shared__ double cta_sum[32][NV];
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const int step = static_cast<int>(csize) * FIN_SLICES;
   double acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = 0.0;
   if (active) {
-    int q = threadIdx.y;
-    for (; q + 3 * FIN_SLICES < parts; q += 4 * FIN_SLICES) {       // 4 x NV independent loads in flight
+    int q = static_cast<int>(crank) * FIN_SLICES + threadIdx.y;
+    for (; q + 3 * step < parts; q += 4 * step) {                    // 4 x NV independent loads in flight
       float t[4][NV];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) t[u][v] = partial[static_cast<size_t>(q + u * FIN_SLICES) * stride + offs[v]];
+        for (int v = 0; v < NV; ++v) t[u][v] = partial[static_cast<size_t>(q + u * step) * stride + offs[v]];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] += static_cast<double>(t[u][v]);
     }
-    for (; q < parts; q += FIN_SLICES) {
+    for (; q < parts; q += step) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) acc[v] += static_cast<double>(partial[static_cast<size_t>(q) * stride + offs[v]]);
     }
@@ -78,13 +111,51 @@ __device__ __forceinline__ void reduce_parts(const float* __restrict__ partial, 
 #pragma unroll
   for (int v = 0; v < NV; ++v) sh[threadIdx.y][threadIdx.x][v] = acc[v];
   __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double t = 0.0;
+      for (int y = 0; y < FIN_SLICES; ++y) t += sh[y][threadIdx.x][v];
+      cta_sum[threadIdx.x][v] = t;
+    }
+  }
+  cluster_sync_all();                                               // every CTA's cta_sum is written and visible
+  const bool owner = (crank == 0) && (threadIdx.y == 0);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     double t = 0.0;
-    if (threadIdx.y == 0)
-      for (int y = 0; y < FIN_SLICES; ++y) t += sh[y][threadIdx.x][v];
+    if (owner)
+      for (uint32_t r = 0; r < csize; ++r) t += ld_dsmem_f64(&cta_sum[threadIdx.x][v], r);
     out[v] = t;
   }
+  cluster_sync_all();                                               // nobody exits while rank 0 still reads its memory
+  return owner;
+}
+
+// Launch a finalize kernel with cluster dims (1, cy, 1) over grid (gx, cy): cy CTAs share one column block.
+static int finalize_cluster_y(int parts) {
+  int cy = (parts + FIN_SLICES - 1) / FIN_SLICES;
+  if (cy < 1) cy = 1;
+  if (cy > FIN_MAX_CLUSTER) cy = FIN_MAX_CLUSTER;
+  while (cy & (cy - 1)) cy &= cy - 1;                               // power of two <= 8
+  return cy;
+}
+template <typename... KArgs, typename... Args>
+static int launch_finalize(void (*kernel)(KArgs...), int gx, int cy, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(gx, cy, 1);
+  cfg.blockDim = dim3(32, FIN_SLICES, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = cy;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CGCN_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  return CGCN_OK;
 }
 
 // ------------------------------------------------------------------------------- gate forward
@@ -119,7 +190,7 @@ __global__ void __launch_bounds__(RW_THREADS) gate_fwd_kernel(const GateFwdArgs 
         dot += dot4(z[v], wg[v]);
       }
       dot = warp_sum(dot);
-      const float g = sigmoidf_(dot + bg);
+      const float g = a.gate_off ? 1.0f : sigmoidf_(dot + bg);
       const float omg = 1.0f - g;
       if (lane == 0) a.g[static_cast<size_t>(row) * S + s] = g;
 #pragma unroll
@@ -166,7 +237,7 @@ bn_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, int 
   const bool active = c < D;
   const int K = 2 * S * D;
   if (!training) {
-    if (active && threadIdx.y == 0) {
+    if (active && threadIdx.y == 0 && blockIdx.y == 0) {
       const float m = running_mean[c];
       const float r = static_cast<float>(1.0 / sqrt(static_cast<double>(running_var[c]) + static_cast<double>(eps)));
       for (int s = 0; s < S; ++s) {
@@ -183,13 +254,14 @@ bn_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, int 
     offs[2 * s + 1] = (1 * S + s) * D + c;
   }
   double sums[2 * S];
+  bool owner = threadIdx.y == 0 && blockIdx.y == 0;
   if (presummed != nullptr) {                       // row-partitioned mode: sums already reduced over CTAs and ranks
 #pragma unroll
     for (int v = 0; v < 2 * S; ++v) sums[v] = active ? presummed[offs[v]] : 0.0;
   } else {
-    reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
+    owner = reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
   }
-  if (!active || threadIdx.y != 0) return;
+  if (!active || !owner) return;
   if (sums_out != nullptr) {                        // row-partitioned mode, first half: publish this rank's sums
 #pragma unroll
     for (int v = 0; v < 2 * S; ++v) sums_out[offs[v]] = sums[v];
@@ -293,13 +365,14 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, 
     offs[2 * s + 1] = (1 * S + s) * D + c;
   }
   double sums[2 * S];
+  bool owner = threadIdx.y == 0 && blockIdx.y == 0;
   if (presummed != nullptr) {
 #pragma unroll
     for (int v = 0; v < 2 * S; ++v) sums[v] = active ? presummed[offs[v]] : 0.0;
   } else {
-    reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
+    owner = reduce_parts<2 * S>(partial, parts, K, offs, active, sums);
   }
-  if (!active || threadIdx.y != 0) return;
+  if (!active || !owner) return;
   if (presummed != nullptr) {                       // second half: c1 / c2 from the all-reduced sums; d gamma / d beta stay local
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -421,8 +494,8 @@ __global__ void __launch_bounds__(32 * FIN_SLICES) col_finalize_kernel(const Col
   const bool active = q >= 0;
   int offs[1] = {active ? a.begin[q] + local : 0};
   double out[1];
-  reduce_parts<1>(a.partial, a.parts, a.stride, offs, active, out);
-  if (active && threadIdx.y == 0) a.dst[q][local] = static_cast<float>(out[0]);
+  const bool owner = reduce_parts<1>(a.partial, a.parts, a.stride, offs, active, out);
+  if (active && owner) a.dst[q][local] = static_cast<float>(out[0]);
 }
 
 // ------------------------------------------------------------------------------ generic column sum
@@ -642,13 +715,13 @@ int gate_fwd_launch(const GateFwdArgs& a, int d, int S, bool stats, int* grid_ou
 int bn_finalize_launch(const float* partial, int parts, int64_t n, int S, int D, float eps, float momentum, int training,
                        float* running_mean, float* running_var, int64_t* nbt, float* mean_out, float* rstd_out,
                        const double* presummed, double* sums_out, cudaStream_t stream) {
-  const dim3 blk(32, FIN_SLICES);
+  const int cy = (training && presummed == nullptr) ? finalize_cluster_y(parts) : 1;
   if (S == 1)
-    bn_finalize_kernel<1><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, eps, momentum, training, running_mean,
-                                                             running_var, nbt, mean_out, rstd_out, presummed, sums_out);
+    CGCN_TRY(launch_finalize(bn_finalize_kernel<1>, (D + 31) / 32, cy, stream, partial, parts, n, D, eps, momentum, training,
+                             running_mean, running_var, nbt, mean_out, rstd_out, presummed, sums_out));
   else
-    bn_finalize_kernel<2><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, eps, momentum, training, running_mean,
-                                                             running_var, nbt, mean_out, rstd_out, presummed, sums_out);
+    CGCN_TRY(launch_finalize(bn_finalize_kernel<2>, (D + 31) / 32, cy, stream, partial, parts, n, D, eps, momentum, training,
+                             running_mean, running_var, nbt, mean_out, rstd_out, presummed, sums_out));
   return check_launch("bn_finalize_kernel");
 }
 
@@ -672,13 +745,13 @@ int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, 
 
 int bn_bwd_finalize_launch(const float* partial, int parts, int64_t n, int S, int D, int training, float* c1, float* c2,
                            float* dgamma, float* dbeta, const double* presummed, double* sums_out, cudaStream_t stream) {
-  const dim3 blk(32, FIN_SLICES);
+  const int cy = (presummed == nullptr) ? finalize_cluster_y(parts) : 1;
   if (S == 1)
-    bn_bwd_finalize_kernel<1><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, training, c1, c2, dgamma, dbeta,
-                                                                 presummed, sums_out);
+    CGCN_TRY(launch_finalize(bn_bwd_finalize_kernel<1>, (D + 31) / 32, cy, stream, partial, parts, n, D, training, c1, c2,
+                             dgamma, dbeta, presummed, sums_out));
   else
-    bn_bwd_finalize_kernel<2><<<(D + 31) / 32, blk, 0, stream>>>(partial, parts, n, D, training, c1, c2, dgamma, dbeta,
-                                                                 presummed, sums_out);
+    CGCN_TRY(launch_finalize(bn_bwd_finalize_kernel<2>, (D + 31) / 32, cy, stream, partial, parts, n, D, training, c1, c2,
+                             dgamma, dbeta, presummed, sums_out));
   return check_launch("bn_bwd_finalize_kernel");
 }
 
@@ -713,7 +786,7 @@ int gate_bwd_finalize_launch(const float* partial, int grid, int d, float* db, f
   f.dst[0] = db;  f.begin[0] = 0;      f.len[0] = d;
   f.dst[1] = dwg; f.begin[1] = d;      f.len[1] = d;
   f.dst[2] = dbg; f.begin[2] = 2 * d;  f.len[2] = 1;
-  col_finalize_kernel<<<(2 * d + 1 + 31) / 32, dim3(32, FIN_SLICES), 0, stream>>>(f);
+  CGCN_TRY(launch_finalize(col_finalize_kernel, (2 * d + 1 + 31) / 32, finalize_cluster_y(grid), stream, f));
   return check_launch("col_finalize_kernel");
 }
 
@@ -735,7 +808,7 @@ int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* dst, fl
   f.parts = parts;
   f.stride = 128;
   f.dst[0] = dst; f.begin[0] = 0; f.len[0] = cols;
-  col_finalize_kernel<<<(cols + 31) / 32, dim3(32, FIN_SLICES), 0, stream>>>(f);
+  CGCN_TRY(launch_finalize(col_finalize_kernel, (cols + 31) / 32, finalize_cluster_y(parts), stream, f));
   return check_launch("col_finalize_kernel");
 }
 

@@ -13,6 +13,7 @@ struct GateFwdArgs {
   float* xo;           // [n][S][D]  dropout((1-g) x + g z)
   float* stats_partial;// [grid][2][S][D]  sum relu(xo), sum relu(xo)^2   (STATS only)
   int n;
+  int gate_off;        // extension: g == 1 (x' = z), the gate parameters are not read
   DropoutCfg drop;
 };
 

@@ -258,7 +258,8 @@ class RowPartitionedStep:
                                    fp.views(fp.flat), fp.views(fp.flat_grad) if train else None, bn.running_mean,
                                    bn.running_var, bn.num_batches_tracked, panel_local, input_grad, out, gates,
                                    dout if train else None, ws, model.gemm_impl,
-                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld)
+                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld,
+                                   getattr(model, "gate_off", False))
             m.n_total, m.row_begin = self.n_total, self.parts[self.rank][0]
             m.x_full, m.bn_sums = x_full.data_ptr(), bn_sums.data_ptr()
             pub = C.c_void_p(0)

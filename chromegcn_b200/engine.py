@@ -158,7 +158,8 @@ class ChromosomeEngine:
             m = build_model_struct(graph, d, nclass, layers, S, model.training, model.dropout, seed, step, params,
                                    grads if train else None, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                                    panel, input_grad, out, gates, None, ws, model.gemm_impl,
-                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld)
+                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld,
+                                   getattr(model, "gate_off", False))
             tgt = ops._f32c(target)
             if train:
                 _lib.check(lib.cgcn_train_step(C.byref(m), tgt.data_ptr(), _lib.ptr(probs_out), loss_slot.data_ptr(),

@@ -37,7 +37,8 @@
 extern "C" {
 #endif
 
-#define CGCN_ABI_VERSION 3
+#define CGCN_ABI_VERSION 4
+#define CGCN_MAX_LAYERS 4
 
 typedef void* cgcn_stream_t; /* cudaStream_t */
 
@@ -164,12 +165,13 @@ int cgcn_gemm_gram(const float* A, int64_t lda, const float* B, int64_t ldb, flo
 /* Parameters in the reference's state_dict order and shapes (models/ChromeModels.py:22-31):
  * GC{1,2}.weight [d][d] (in x out), GC{1,2}.bias [d], W{1,2}.weight [1][d], W{1,2}.bias [1],
  * batch_norm.weight/bias [d], out.weight [nclass][d], out.bias [nclass].  A second instance of
- * this struct holds the gradients. */
+ * this struct holds the gradients.  Slots 2.. (GC3/W3, GC4/W4) belong to the variant-sweep extension
+ * (layers > 2); the reference itself never builds more than two layers (models/ChromeModels.py:26-28). */
 typedef struct cgcn_params {
-  float* gc_w[2];
-  float* gc_b[2];
-  float* gate_w[2];
-  float* gate_b[2];
+  float* gc_w[CGCN_MAX_LAYERS];
+  float* gc_b[CGCN_MAX_LAYERS];
+  float* gate_w[CGCN_MAX_LAYERS];
+  float* gate_b[CGCN_MAX_LAYERS];
   float* bn_w;
   float* bn_b;
   float* out_w;
@@ -180,7 +182,7 @@ typedef struct cgcn_model {
   cgcn_graph graph;
   int32_t d;              /* feature width, multiple of 128 */
   int32_t nclass;         /* <= 128 */
-  int32_t layers;         /* 1 or 2 (the reference builds 2 iff gcn_layers == 2) */
+  int32_t layers;         /* 1 or 2 (the reference builds 2 iff gcn_layers == 2); 3..CGCN_MAX_LAYERS = extension */
   int32_t strands;        /* 1 = one forward() call; 2 = x_f and x_r of finetune.py:41-42 batched */
   int32_t training;       /* BatchNorm batch statistics + dropout (ChromeModel.train()) */
   int32_t gemm_impl;      /* see above */
@@ -192,6 +194,9 @@ typedef struct cgcn_model {
   float bn_momentum;      /* 0.1 */
   float bn_eps;           /* 1e-5 */
   int32_t row_begin;      /* row-partitioned graphs: global index of the first local row (dropout stream position) */
+  int32_t gate_off;       /* extension (variant sweep "gate off"; the reference ignores its gate argument,
+                             models/ChromeModels.py:22-31): 1 = every layer is x <- tanh(A_hat x W + b), g == 1 */
+  int32_t reserved0;
   uint64_t seed;          /* dropout: keep-mask is a pure function of (seed, step, site, element) */
   uint64_t step;
   cgcn_params params;
@@ -202,7 +207,7 @@ typedef struct cgcn_model {
   const float* x_in;      /* [n][strands][d] */
   float* x_in_grad;       /* [n][strands][d] or NULL */
   float* out;             /* [n][strands][out_ld] logits in the first nclass columns (models/ChromeModels.py:51) */
-  float* gate[2];         /* [n][strands] g, g2 (models/ChromeModels.py:39,45) */
+  float* gate[CGCN_MAX_LAYERS]; /* [n][strands] g, g2 (models/ChromeModels.py:39,45) */
   const float* out_grad;  /* [n][strands][out_ld], input of backward */
   float* workspace;       /* cgcn_model_workspace_bytes() bytes, kept from forward to backward */
   size_t workspace_bytes;

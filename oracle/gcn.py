@@ -86,6 +86,47 @@ class ChromeGCNOracle(nn.Module):
         return x_in, out, (g, g2), None
 
 
+class ChromeGCNExtOracle(nn.Module):
+    """EXTENSION oracle (no reference pin): the variant sweep of BASELINE.json asks for "gcn_layers 3" and
+    "gate off", which models/ChromeModels.py cannot express (its `gate` argument is ignored, :22-31, and any
+    `layers != 2` builds one layer, :26-28).  This is the natural generalisation of models/ChromeModels.py:37-46:
+    the per-layer recipe `z = tanh(GC_l(x)); g = sigmoid(W_l z); x = (1-g) x + g z` repeated `layers` times with
+    dropout between consecutive layers, and with `gate=False` simply `x = z`.  For `layers in (1, 2), gate=True`
+    it is the reference model exactly (checked in tests/test_oracle_golden.py against ChromeGCNOracle).
+    `dropout_masks`: one mask per inter-layer site (layers-1 of them) followed by the head mask."""
+
+    def __init__(self, nfeat: int, nhid: int, nclass: int, dropout: float, gate: bool = True, layers: int = 2):
+        super().__init__()
+        self.num_layers, self.gate = int(layers), bool(gate)
+        for l in range(1, self.num_layers + 1):
+            setattr(self, "GC%d" % l, GraphConvolutionOracle(nfeat, nhid))
+            setattr(self, "W%d" % l, nn.Linear(nfeat, 1))
+        self.dropout = dropout
+        self.batch_norm = nn.BatchNorm1d(nfeat)
+        self.out = nn.Linear(nfeat, nclass)
+
+    def forward(self, x_in, adj, deg=None, src_dict=None, return_gate=False,
+                dropout_masks: Optional[Sequence[Optional[torch.Tensor]]] = None):
+        masks = list(dropout_masks) if dropout_masks is not None else [None] * self.num_layers
+        x, gates = x_in, []
+        for l in range(1, self.num_layers + 1):
+            if l > 1:
+                m = masks[l - 2]
+                x = x * m if m is not None else F.dropout(x, self.dropout, training=self.training)
+            z = torch.tanh(getattr(self, "GC%d" % l)(x, adj))
+            if self.gate:
+                g = torch.sigmoid(getattr(self, "W%d" % l)(z))
+                x = (1 - g) * x + g * z
+            else:
+                g = torch.ones(z.shape[0], 1, dtype=z.dtype)
+                x = z
+            gates.append(g)
+        x = self.batch_norm(F.relu(x))
+        m = masks[self.num_layers - 1]
+        x = x * m if m is not None else F.dropout(x, self.dropout, training=self.training)
+        return x_in, self.out(x), tuple(gates), None
+
+
 def coo_adjacency(indptr, indices, dtype=torch.float32) -> torch.Tensor:
     """The torch sparse COO tensor `process_graph('hic', ...)` returns
     (utils/util_methods.py:120-135,177-178): int64 indices, fp32 values, not coalesced."""
@@ -164,14 +205,14 @@ def stress_init_(model: nn.Module, seed: int = 7):
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for name, p in model.named_parameters():
-            if name.endswith("GC1.weight") or name.endswith("GC2.weight"):
+            if name.startswith("GC") and name.endswith(".weight"):
                 fan = p.shape[0] + p.shape[1]
                 p.copy_(torch.randn(p.shape, generator=g) * (2.0 / fan) ** 0.5)
             elif name == "batch_norm.weight":
                 p.copy_(1.0 + 0.2 * torch.randn(p.shape, generator=g))
             elif name.endswith("bias"):
                 p.copy_(0.1 * torch.randn(p.shape, generator=g))
-            elif name in ("W1.weight", "W2.weight"):
+            elif name.startswith("W") and name.endswith(".weight"):
                 p.copy_(torch.randn(p.shape, generator=g) * 0.3)
             elif name == "out.weight":
                 p.copy_(torch.randn(p.shape, generator=g) * 0.1)

@@ -348,3 +348,63 @@ def test_eval_from_reference_weights_auroc_aupr(gemm_impl):
     a1, r1 = _auc_aupr(t.numpy(), probs.cpu().numpy())
     a2, r2 = _auc_aupr(t.numpy(), ref)
     assert np.abs(a1 - a2).max() <= 1e-4 and np.abs(r1 - r2).max() <= 1e-4
+
+
+@pytest.mark.parametrize("layers,gate", [(3, True), (2, False), (3, False), (4, True), (1, False)])
+def test_extension_variants_match_oracle(layers, gate):
+    """Variant sweep of BASELINE.json ("gcn_layers 3", "gate off"): `ChromeGCN(..., extended=True)` against the
+    extension oracle in fp64, train mode with dropout (keep-masks injected), fused two-strand step with input
+    gradients.  Same tolerances as the reference-pinned tests."""
+    from chromegcn_b200 import ops
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.engine import ChromosomeEngine
+    z = np.load(os.path.join(GOLDEN, "model_l2_stress.npz"))
+    x_f, x_r, tgt = (torch.from_numpy(z[k]) for k in ("x_f", "x_r", "target"))
+    n, c = tgt.shape
+    p = 0.2
+    torch.manual_seed(11)
+    om = ogcn.stress_init_(ogcn.ChromeGCNExtOracle(128, 128, c, p, gate, layers), seed=5)
+    m = ChromeGCN(128, 128, c, p, gate, layers, extended=True)
+    missing = m.load_state_dict(om.state_dict())
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert m.num_layers == layers and m.gate_off == (not gate)
+    m = m.to(_dev()).train()
+    g = _graph(z)
+    eng = ChromosomeEngine(m, 2)
+    probs = torch.empty(n, c, device=_dev())
+    loss = torch.zeros(1, device=_dev())
+    panel = eng.pack(x_f.to(_dev()), x_r.to(_dev()))
+    xg = torch.empty_like(panel)
+    out, gates = eng.run(g, panel, tgt.to(_dev()), probs, loss, train=True, input_grad=xg)
+    seed, step = m._drop_seed, m._drop_step
+    sites = [0 if l == 0 else l + 1 for l in range(layers - 1)] + [1]  # after layer 1, after layer l+1 ..., after BatchNorm
+    masks = [ops.dropout_mask(n, 2, 128, p, seed, step, s).cpu().double() for s in sites]
+    if layers >= 3:
+        assert not torch.equal(masks[0], masks[1])                     # every site draws its own mask
+    om = om.double().train()
+    adj = ogcn.coo_adjacency(z["indptr"], z["indices"], torch.float64)
+    lo, prob_o, pred_o, ex = ogcn.chromosome_step(om, x_f.double(), x_r.double(), tgt.double(), adj, None, True,
+                                                  masks_f=[mk[:, 0] for mk in masks], masks_r=[mk[:, 1] for mk in masks],
+                                                  input_grads=True)
+    assert ogcn.max_rel(out.mean(1).cpu(), pred_o) <= FWD_TOL
+    assert ogcn.max_rel(probs.cpu(), prob_o) <= FWD_TOL
+    assert abs(loss.item() - lo) <= FWD_TOL * abs(lo)
+    assert len(gates) == layers
+    for l in range(layers):
+        assert ogcn.max_rel(gates[l][:, 0].cpu(), ex["gates_f"][l][:, 0]) <= FWD_TOL
+    for (k, pp), (_, q) in zip(m.named_parameters(), om.named_parameters()):
+        if q.grad is None:                                             # gate parameters of a gate-off model
+            assert float(pp.grad.abs().max()) == 0.0, k
+            continue
+        err = ogcn.max_rel(pp.grad.cpu(), q.grad)
+        assert err <= 5e-5, (k, err)
+    assert ogcn.max_rel(xg[:, 0].cpu(), ex["x_f"].grad) <= 5e-5
+    assert ogcn.max_rel(xg[:, 1].cpu(), ex["x_r"].grad) <= 5e-5
+    # module API (one strand, autograd) agrees with the fused step's forward in eval mode
+    m.eval()
+    om.eval()
+    with torch.no_grad():
+        _, o1, (g1, g2), _ = m(x_f.to(_dev()), g, None)
+        _, o2, og, _ = om(x_f.double(), adj)
+    assert ogcn.max_rel(o1.cpu(), o2) <= FWD_TOL
+    assert (g2 is None) == (layers == 1) and len(m.last_gates) == layers

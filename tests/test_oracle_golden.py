@@ -126,3 +126,50 @@ def test_process_graph_all_adj_types(golden_dir):
     # 'both' is genuinely weighted: values differ inside a row
     r, c, v = oadj.process_graph_general("both", z["indptr"], z["indices"], n)
     assert any(len(set(v[r == i].tolist())) > 1 for i in range(n))
+
+
+@pytest.mark.parametrize("tag", ["l2_stress", "l1_stress"])
+def test_extension_oracle_reduces_to_reference_model(golden_dir, tag):
+    """ChromeGCNExtOracle (layers / gate honoured: the variant-sweep extension) with layers in (1, 2) and the gate
+    on IS the reference model: bit-identical forward and gradients on the golden inputs."""
+    z = np.load(os.path.join(golden_dir, "model_%s.npz" % tag))
+    layers = int(z["layers"])
+    x_f, x_r, tgt = (torch.from_numpy(z[k]) for k in ("x_f", "x_r", "target"))
+    adj = ogcn.coo_adjacency(z["indptr"], z["indices"])
+    ref = _load_model(z, layers).train()
+    ext = ogcn.ChromeGCNExtOracle(128, 128, tgt.shape[1], 0.0, True, layers)
+    ext.load_state_dict(ref.state_dict())
+    ext.train()
+    l0, _, p0, _ = ogcn.chromosome_step(ref, x_f, x_r, tgt, adj, None, True)
+    l1, _, p1, _ = ogcn.chromosome_step(ext, x_f, x_r, tgt, adj, None, True)
+    assert l0 == l1 and torch.equal(p0, p1)
+    for (k, a), (_, b) in zip(ref.named_parameters(), ext.named_parameters()):
+        assert torch.equal(a.grad, b.grad), k
+
+
+def test_extension_oracle_gate_off_and_three_layers():
+    """Definitions of the two extension variants: gate off is x <- tanh(GC(x)) with g == 1 and no gradient to W_l;
+    three layers chain the same recipe."""
+    torch.manual_seed(3)
+    n, c = 40, 5
+    ip = np.arange(0, 2 * n + 1, 2, dtype=np.int32)
+    ix = np.stack([(np.arange(n) + 1) % n, (np.arange(n) + 7) % n], 1).astype(np.int32)
+    ix.sort(axis=1)
+    sym = {(i, int(j)) for i in range(n) for j in ix[i]} | {(int(j), i) for i in range(n) for j in ix[i]}
+    rows = [[j for (i2, j) in sorted(sym) if i2 == i] for i in range(n)]
+    ip = np.cumsum([0] + [len(r) for r in rows]).astype(np.int32)
+    ix = np.concatenate(rows).astype(np.int32)
+    adj = ogcn.coo_adjacency(ip, ix, torch.float64)
+    x = torch.randn(n, 128, dtype=torch.float64)
+    m = ogcn.stress_init_(ogcn.ChromeGCNExtOracle(128, 128, c, 0.0, False, 3)).double().train()
+    _, out, gates, _ = m(x, adj)
+    assert len(gates) == 3 and all(torch.equal(g, torch.ones(n, 1, dtype=torch.float64)) for g in gates)
+    h = x
+    for l in (1, 2, 3):
+        h = torch.tanh(torch.spmm(adj, h @ getattr(m, "GC%d" % l).weight) + getattr(m, "GC%d" % l).bias)
+    m.eval()
+    m.batch_norm.train()
+    ref = m.out(m.batch_norm(torch.relu(h)))
+    assert ogcn.max_rel(out, ref) <= 1e-12
+    out.sum().backward()
+    assert all(getattr(m, "W%d" % l).weight.grad is None for l in (1, 2, 3))
