@@ -13,6 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libchromegcn.so")
 ABI_VERSION = 4
 MAX_LAYERS = 4
+MAX_PEERS = 8
 
 
 class ChromeGCNNativeError(RuntimeError):
@@ -43,7 +44,12 @@ class Model(C.Structure):
                 ("x_in", C.c_void_p), ("x_in_grad", C.c_void_p), ("out", C.c_void_p), ("gate", C.c_void_p * MAX_LAYERS),
                 ("out_grad", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("stream", C.c_void_p),
-                ("n_total", C.c_int64), ("x_full", C.c_void_p), ("bn_sums", C.c_void_p)]
+                ("n_total", C.c_int64), ("x_full", C.c_void_p), ("bn_sums", C.c_void_p), ("peer", C.c_void_p)]
+
+
+class PeerPanel(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("row_begin", C.c_int32 * (MAX_PEERS + 1)),
+                ("base", C.c_void_p * MAX_PEERS)]
 
 
 _P = C.c_void_p
@@ -64,6 +70,12 @@ PROTOTYPES = {
     "cgcn_coo_to_pattern_workspace_bytes": (C.c_int, [_I64, _I64, C.POINTER(_SZ)]),
     "cgcn_coo_to_pattern": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, C.POINTER(_I32), _P, _SZ, _P]),
     "cgcn_spmm": (C.c_int, [C.POINTER(Graph), _P, _P, _I32, _I32, _P, _P]),
+    "cgcn_spmm_peer": (C.c_int, [C.POINTER(Graph), C.POINTER(PeerPanel), _P, _I32, _I32, _P, _P]),
+    "cgcn_peer_alloc": (C.c_int, [_SZ, C.POINTER(_P), C.c_char_p]),
+    "cgcn_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "cgcn_peer_close": (C.c_int, [_P]),
+    "cgcn_peer_free": (C.c_int, [_P]),
+    "cgcn_peer_publish": (C.c_int, [_P, _P, _SZ, _P]),
     "cgcn_gemm_rowpanel": (C.c_int, [_P, _I64, _P, _I32, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _I32, _I32, _P, _SZ, _P]),
     "cgcn_gemm_gram_workspace_bytes": (_SZ, [_I64]),
     "cgcn_gemm_gram": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P, _SZ, _P]),
@@ -100,7 +112,7 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.cgcn_abi_version() != ABI_VERSION:
         raise ChromeGCNNativeError("libchromegcn.so ABI %d != binding ABI %d" % (lib.cgcn_abi_version(), ABI_VERSION))
-    for which, st in ((0, Graph), (1, Params), (2, Model)):
+    for which, st in ((0, Graph), (1, Params), (2, Model), (3, PeerPanel)):
         if lib.cgcn_sizeof(which) != C.sizeof(st):
             raise ChromeGCNNativeError("struct %s: C sizeof %d != ctypes sizeof %d" %
                                        (st.__name__, lib.cgcn_sizeof(which), C.sizeof(st)))

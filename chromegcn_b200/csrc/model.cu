@@ -18,6 +18,8 @@ namespace cgcn {
 // ---- declarations of the launchers defined in the other translation units
 int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int scale_mode, const float* residual,
                 cudaStream_t stream);
+int spmm_peer_launch(const cgcn_graph* g, const cgcn_peer_panel* pp, float* out, int width, int scale_mode,
+                     const float* residual, cudaStream_t stream);
 int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                        int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
                        cudaStream_t stream);
@@ -306,7 +308,10 @@ static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
   float* ws = c.ws;
   const float* xin = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
   // ax = A_hat x                                   (torch.spmm, models/SubLayers.py:46)
-  CGCN_TRY(spmm_launch(&m->graph, gather_src, ws + lay.ax[l], c.W, 1, nullptr, c.st));
+  if (c.dist && m->peer != nullptr)  // neighbour rows straight from the owners' exchange buffers (NVLink loads)
+    CGCN_TRY(spmm_peer_launch(&m->graph, m->peer, ws + lay.ax[l], c.W, 1, nullptr, c.st));
+  else
+    CGCN_TRY(spmm_launch(&m->graph, gather_src, ws + lay.ax[l], c.W, 1, nullptr, c.st));
   // y = ax W + b                                   (torch.mm + bias, models/SubLayers.py:43,50)
   CGCN_TRY(gemm_rowpanel_dispatch(ws + lay.ax[l], c.d, m->params.gc_w[l], 0, m->params.gc_b[l], ws + lay.z[l], c.d, c.M, c.d,
                                   c.d, nullptr, nullptr, 1, m->gemm_impl, c.tcws, lay.tc_bytes, c.st, fwd_image(c, l)));
@@ -450,6 +455,7 @@ static int bwd_head(const Ctx& c, Fork& f) {
 // its all-gathered copy)
 static int bwd_propagate(const Ctx& c, int l_from, const float* t_gather) {
   float* dx = (l_from == 0) ? c.m->x_in_grad : bwd_other(c, l_from);
+  if (c.dist && c.m->peer != nullptr) return spmm_peer_launch(&c.m->graph, c.m->peer, dx, c.W, 0, c.ws + c.lay.dC, c.st);
   return spmm_launch(&c.m->graph, t_gather, dx, c.W, 0, c.ws + c.lay.dC, c.st);
 }
 
@@ -520,8 +526,8 @@ static int model_backward(const cgcn_model* m) {
 static int model_phase(const cgcn_model* m, int kind, int layer, const float** publish) {
   if (publish) *publish = nullptr;
   CGCN_TRY(validate(m, kind >= CGCN_PHASE_BWD_HEAD));
-  CGCN_REQUIRE(m->n_total >= m->graph.n && m->x_full != nullptr && m->bn_sums != nullptr && m->row_begin >= 0,
-               "cgcn_model_phase: needs n_total, row_begin, x_full and bn_sums");
+  CGCN_REQUIRE(m->n_total >= m->graph.n && (m->x_full != nullptr || m->peer != nullptr) && m->bn_sums != nullptr && m->row_begin >= 0,
+               "cgcn_model_phase: needs n_total, row_begin, x_full (or peer) and bn_sums");
   CGCN_REQUIRE(layer >= 0 && layer < m->layers, "cgcn_model_phase: layer %d", layer);
   const Ctx c = make_ctx(m);
   Fork f;
@@ -582,6 +588,7 @@ extern "C" size_t cgcn_sizeof(int32_t which) {
     case 0: return sizeof(cgcn_graph);
     case 1: return sizeof(cgcn_params);
     case 2: return sizeof(cgcn_model);
+    case 3: return sizeof(cgcn_peer_panel);
     default: return 0;
   }
 }

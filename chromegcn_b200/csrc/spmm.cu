@@ -14,6 +14,8 @@
 // 128-bit loads per lane are kept in flight.  Summation runs in CSR (ascending column) order,
 // so results are run-to-run deterministic.  Rows longer than LONG_ROW are split over the
 // 8 warps of the CTA and combined in shared memory in a fixed order.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace cgcn {
@@ -163,6 +165,205 @@ spmm_pattern_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Peer-memory variant: the gathered panel is spread over the exchange buffers of the ranks that share one
+// row-partitioned graph (cgcn_peer_panel).  Same warp-per-row schedule; each lane resolves the owner of ITS
+// column index once (<= 7 compares against the block boundaries) into a row pointer, and the 64-bit pointer is
+// what gets broadcast by shuffle.  Rows owned by this rank come from local HBM / L2, the others arrive as NVLink
+// loads from the owner's memory -- there is no all-gathered copy of the panel.
+struct PeerTable {
+  const float* base[CGCN_MAX_PEERS];
+  int begin[CGCN_MAX_PEERS + 1];
+  int world;
+};
+
+template <int VEC>
+__device__ __forceinline__ const float* peer_row(const PeerTable& t, int c) {
+  int o = 0;
+#pragma unroll
+  for (int r = 1; r < CGCN_MAX_PEERS; ++r) o += (r < t.world && c >= t.begin[r]) ? 1 : 0;
+  return t.base[o] + static_cast<size_t>(c - t.begin[o]) * (static_cast<size_t>(VEC) * 128);
+}
+
+__device__ __forceinline__ const float* shfl_ptr(const float* p, int src) {
+  const unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(v), src);
+  const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(v >> 32), src);
+  return reinterpret_cast<const float*>((static_cast<unsigned long long>(hi) << 32) | lo);
+}
+
+template <int VEC>
+__device__ __forceinline__ void gather_range_peer(const int32_t* __restrict__ colidx, const PeerTable& t, int begin, int end,
+                                                  int lane, float4 (&acc)[VEC]) {
+  constexpr int UNROLL = (VEC >= 8) ? 1 : (8 / VEC);
+  for (int base = begin; base < end; base += 32) {
+    const bool have = base + lane < end;
+    const float* mine = have ? peer_row<VEC>(t, __ldg(colidx + base + lane)) : t.base[0];
+    const int cnt = min(32, end - base);
+    int k = 0;
+    for (; k + UNROLL <= cnt; k += UNROLL) {
+      float4 v[UNROLL][VEC];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const float* p = shfl_ptr(mine, k + u) + lane * 4;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) v[u][q] = ldg4(p + q * 128);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          acc[q].x += v[u][q].x;
+          acc[q].y += v[u][q].y;
+          acc[q].z += v[u][q].z;
+          acc[q].w += v[u][q].w;
+        }
+    }
+    for (; k < cnt; ++k) {
+      const float* p = shfl_ptr(mine, k) + lane * 4;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        const float4 v = ldg4(p + q * 128);
+        acc[q].x += v.x;
+        acc[q].y += v.y;
+        acc[q].z += v.z;
+        acc[q].w += v.w;
+      }
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(SPMM_WARPS * 32, (VEC <= 2) ? 5 : 2)
+spmm_peer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n, const PeerTable t,
+                 float* __restrict__ out, int scale_mode, const float* __restrict__ residual) {
+  constexpr size_t PITCH = static_cast<size_t>(VEC) * 128;
+  __shared__ float4 red[SPMM_WARPS][VEC][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * SPMM_WARPS;
+  const int row = row0 + warp;
+  int start = 0, end = 0;
+  if (row < n) {
+    start = __ldg(rowptr + row);
+    end = __ldg(rowptr + row + 1);
+  }
+  const int deg = end - start;
+  auto finish = [&](float4 (&acc)[VEC], int r, int d) {
+    const float s = (scale_mode != 1) ? 1.0f : (d > 0 ? __fdiv_rn(1.0f, static_cast<float>(d)) : 1.0f);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      float4 v = make_float4(acc[q].x * s, acc[q].y * s, acc[q].z * s, acc[q].w * s);
+      if (residual != nullptr) {
+        const float4 e = ldg4(residual + static_cast<size_t>(r) * PITCH + lane * 4 + q * 128);
+        v.x += e.x;
+        v.y += e.y;
+        v.z += e.z;
+        v.w += e.w;
+      }
+      st4(out + static_cast<size_t>(r) * PITCH + lane * 4 + q * 128, v);
+    }
+  };
+  if (row < n && deg <= LONG_ROW) {
+    float4 acc[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_range_peer<VEC>(colidx, t, start, end, lane, acc);
+    finish(acc, row, deg);
+  }
+  const int any_long = __syncthreads_or(row < n && deg > LONG_ROW);
+  if (!any_long) return;
+  for (int r = 0; r < SPMM_WARPS; ++r) {               // hub rows: shared by the 8 warps, fixed-order combine
+    const int lrow = row0 + r;
+    if (lrow >= n) break;
+    const int ls = __ldg(rowptr + lrow), le = __ldg(rowptr + lrow + 1);
+    const int ldeg = le - ls;
+    if (ldeg <= LONG_ROW) continue;
+    const int chunk = (ldeg + SPMM_WARPS - 1) / SPMM_WARPS;
+    const int b = min(ls + warp * chunk, le), e = min(b + chunk, le);
+    float4 acc[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_range_peer<VEC>(colidx, t, b, e, lane, acc);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) red[warp][q][lane] = acc[q];
+    __syncthreads();
+    if (warp == 0) {
+      float4 tot[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        tot[q] = red[0][q][lane];
+        for (int w = 1; w < SPMM_WARPS; ++w) {
+          const float4 u = red[w][q][lane];
+          tot[q].x += u.x;
+          tot[q].y += u.y;
+          tot[q].z += u.z;
+          tot[q].w += u.w;
+        }
+      }
+      finish(tot, lrow, ldeg);
+    }
+    __syncthreads();
+  }
+}
+
+int spmm_peer_launch(const cgcn_graph* g, const cgcn_peer_panel* pp, float* out, int width, int scale_mode,
+                     const float* residual, cudaStream_t stream) {
+  CGCN_REQUIRE(g != nullptr && g->rowptr != nullptr && (g->colidx != nullptr || g->nnz == 0), "cgcn_spmm_peer: null graph");
+  CGCN_REQUIRE(pp != nullptr && out != nullptr, "cgcn_spmm_peer: null panel");
+  CGCN_REQUIRE(pp->world >= 1 && pp->world <= CGCN_MAX_PEERS && pp->rank >= 0 && pp->rank < pp->world,
+               "cgcn_spmm_peer: world=%d rank=%d", pp->world, pp->rank);
+  CGCN_REQUIRE(g->vals == nullptr, "cgcn_spmm_peer: weighted graphs are not row-partitioned");
+  CGCN_REQUIRE(scale_mode == 0 || scale_mode == 1, "cgcn_spmm_peer: scale_mode %d", scale_mode);
+  CGCN_REQUIRE(width > 0 && width % 128 == 0 && width <= 1024, "cgcn_spmm_peer: width %d must be a multiple of 128, <= 1024", width);
+  PeerTable t{};
+  t.world = pp->world;
+  for (int r = 0; r < pp->world; ++r) {
+    CGCN_REQUIRE(pp->base[r] != nullptr && pp->row_begin[r] <= pp->row_begin[r + 1], "cgcn_spmm_peer: bad block %d", r);
+    CGCN_REQUIRE(pp->base[r] != out, "cgcn_spmm_peer: in-place aggregation is not possible");
+    t.base[r] = pp->base[r];
+    t.begin[r] = pp->row_begin[r];
+  }
+  t.begin[pp->world] = pp->row_begin[pp->world];
+  CGCN_REQUIRE(pp->row_begin[pp->rank + 1] - pp->row_begin[pp->rank] == g->n, "cgcn_spmm_peer: graph has %d rows, block %d",
+               g->n, pp->row_begin[pp->rank + 1] - pp->row_begin[pp->rank]);
+  if (g->n <= 0) return CGCN_OK;
+  const dim3 grid((g->n + SPMM_WARPS - 1) / SPMM_WARPS), block(SPMM_WARPS * 32);
+#define PEER_CASE(V)                                                                                              \
+  case V:                                                                                                         \
+    spmm_peer_kernel<V><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, t, out, scale_mode, residual);    \
+    break;
+  switch (width / 128) {
+    PEER_CASE(1)
+    PEER_CASE(2)
+    PEER_CASE(4)
+    PEER_CASE(8)
+    default:
+      set_error("cgcn_spmm_peer: unsupported width %d (128, 256, 512 or 1024)", width);
+      return CGCN_ERR_INVALID;
+  }
+#undef PEER_CASE
+  return check_launch("spmm_peer_kernel");
+}
+
+// ---- exchange buffers (CUDA IPC)
+static int ipc_alloc(size_t bytes, void** ptr, unsigned char* handle) {
+  CGCN_REQUIRE(ptr != nullptr && handle != nullptr && bytes > 0, "cgcn_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  CGCN_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    return CGCN_ERR_CUDA;
+  }
+  memcpy(handle, &h, 64);
+  *ptr = p;
+  return CGCN_OK;
+}
+
 int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int scale_mode, const float* residual,
                 cudaStream_t stream) {
   CGCN_REQUIRE(g != nullptr && g->rowptr != nullptr && (g->colidx != nullptr || g->nnz == 0), "cgcn_spmm: null graph");
@@ -204,4 +405,42 @@ int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int 
 extern "C" int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, int32_t scale_mode,
                          const float* residual, cgcn_stream_t stream) {
   return cgcn::spmm_launch(g, x, out, width, scale_mode, residual, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cgcn_spmm_peer(const cgcn_graph* g, const cgcn_peer_panel* panel, float* out, int32_t width, int32_t scale_mode,
+                              const float* residual, cgcn_stream_t stream) {
+  return cgcn::spmm_peer_launch(g, panel, out, width, scale_mode, residual, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cgcn_peer_alloc(size_t bytes, void** ptr_host, unsigned char handle_host[64]) {
+  return cgcn::ipc_alloc(bytes, ptr_host, handle_host);
+}
+
+extern "C" int cgcn_peer_open(const unsigned char handle_host[64], void** ptr_host) {
+  CGCN_REQUIRE(handle_host != nullptr && ptr_host != nullptr, "cgcn_peer_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, 64);
+  void* p = nullptr;
+  CGCN_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_host = p;
+  return CGCN_OK;
+}
+
+extern "C" int cgcn_peer_close(void* ptr) {
+  if (ptr == nullptr) return CGCN_OK;
+  CGCN_CUDA(cudaIpcCloseMemHandle(ptr));
+  return CGCN_OK;
+}
+
+extern "C" int cgcn_peer_free(void* ptr) {
+  if (ptr == nullptr) return CGCN_OK;
+  CGCN_CUDA(cudaFree(ptr));
+  return CGCN_OK;
+}
+
+extern "C" int cgcn_peer_publish(void* exchange_buffer, const void* local_panel, size_t bytes, cgcn_stream_t stream) {
+  CGCN_REQUIRE(exchange_buffer != nullptr && local_panel != nullptr, "cgcn_peer_publish: null argument");
+  if (bytes == 0) return CGCN_OK;
+  CGCN_CUDA(cudaMemcpyAsync(exchange_buffer, local_panel, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return CGCN_OK;
 }

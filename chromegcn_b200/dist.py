@@ -198,6 +198,84 @@ def allgather_panel(local: torch.Tensor, parts: Sequence[Tuple[int, int]], out: 
     return out
 
 
+# ------------------------------------------------------------------ peer-memory exchange (NVLink loads, no all-gather)
+class PeerExchange:
+    """Exchange buffers of the peer-memory SpMM (`cgcn_spmm_peer`, include/chromegcn.h piece 2b).
+
+    Every rank allocates two `[rows_max, width]` buffers with `cgcn_peer_alloc`, the 64-byte CUDA IPC handles
+    travel through `torch.distributed.all_gather_object`, and every rank maps the others' buffers.  An exchange
+    step is `publish(local_panel)`: a device copy into this rank's current buffer followed by a one-element
+    all-reduce on the stream, which is the cross-rank barrier ("every rank's copy has landed").  The two buffers
+    alternate, so a buffer is only overwritten two exchanges later, when every peer has provably finished reading
+    it (it had to pass the barrier in between) -- one barrier per exchange is enough.  `panel()` is the
+    `cgcn_peer_panel` the next SpMM stage reads.  With world_size 1 no IPC is involved."""
+
+    def __init__(self, parts: Sequence[Tuple[int, int]], rank: int, width: int, device, group=None):
+        import ctypes as C
+        from . import _lib, ops
+        self._lib, self._C = _lib, C
+        lib = _lib.load()
+        self.parts, self.rank, self.width, self.group, self.device = list(parts), rank, width, group, device
+        self.world = len(parts)
+        rows_max = max(e - b for b, e in parts)
+        self.bytes = rows_max * width * 4
+        self.own: List[int] = []
+        self.mapped: List[List[int]] = [[], []]          # [buffer][rank] -> device address
+        self._opened: List[int] = []
+        handles = []
+        with torch.cuda.device(device):
+            for _ in range(2):
+                p, h = C.c_void_p(0), C.create_string_buffer(64)
+                _lib.check(lib.cgcn_peer_alloc(max(self.bytes, 256), C.byref(p), h), "cgcn_peer_alloc")
+                self.own.append(p.value)
+                handles.append(h.raw)
+            if self.world > 1:
+                gathered: List = [None] * self.world
+                dist.all_gather_object(gathered, handles, group=group)
+            else:
+                gathered = [handles]
+            for k in range(2):
+                for r in range(self.world):
+                    if r == rank:
+                        self.mapped[k].append(self.own[k])
+                    else:
+                        p = C.c_void_p(0)
+                        _lib.check(lib.cgcn_peer_open(gathered[r][k], C.byref(p)), "cgcn_peer_open(rank %d)" % r)
+                        self.mapped[k].append(p.value)
+                        self._opened.append(p.value)
+        begins = [b for b, _ in parts] + [parts[-1][1]]
+        self._panels = [ops.peer_panel(self.mapped[k], begins, rank) for k in range(2)]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.cur = 0
+        self.exchanges = 0
+
+    def publish(self, local_ptr: int, nbytes: int) -> None:
+        lib = self._lib.load()
+        self.cur ^= 1
+        self._lib.check(lib.cgcn_peer_publish(self.own[self.cur], local_ptr, nbytes, self._lib.current_stream()),
+                        "cgcn_peer_publish")
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)            # stream-ordered cross-rank barrier
+        self.exchanges += 1
+
+    def panel(self):
+        return self._panels[self.cur]
+
+    def close(self) -> None:
+        lib = self._lib.load()
+        if self.world > 1 and dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)                            # nobody unmaps / frees memory a peer still reads
+        for p in self._opened:
+            lib.cgcn_peer_close(p)
+        self._opened = []
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self.own:
+            lib.cgcn_peer_free(p)
+        self.own = []
+
+
 # ------------------------------------------------------------------ row-partitioned train step (one huge graph)
 PHASE_FWD_LAYER, PHASE_FWD_HEAD, PHASE_BWD_HEAD, PHASE_BWD_LAYER, PHASE_BWD_INPUT = 0, 1, 2, 3, 4
 
@@ -209,15 +287,29 @@ class RowPartitionedStep:
     (SURVEY.md 8(e)): all-gather of the panel the next SpMM reads (L forward + L-1 backward, +1 with input
     gradients), all-reduce of the BatchNorm column sums (forward and backward), and one all-reduce of the flat
     gradient buffer + loss at the end.  With world_size 1 the collectives are identities and the result is the
-    single-GPU step."""
+    single-GPU step.
 
-    def __init__(self, model, graph_local, parts: Sequence[Tuple[int, int]], rank: int, strands: int = 2, group=None):
+    `exchange="peer"` (the B200 path) replaces every panel all-gather by `PeerExchange.publish` + the peer-memory
+    SpMM: neighbour rows are NVLink loads from the owner's exchange buffer inside the kernel, nothing is
+    materialised.  `exchange="nccl"` is the all-gather formulation."""
+
+    def __init__(self, model, graph_local, parts: Sequence[Tuple[int, int]], rank: int, strands: int = 2, group=None,
+                 exchange: str = "nccl"):
         from .engine import ChromosomeEngine
         self.model, self.graph, self.parts, self.rank, self.S, self.group = model, graph_local, list(parts), rank, strands, group
         self.engine = ChromosomeEngine(model, strands)
         self.n_total = parts[-1][1]
         self.n_local = parts[rank][1] - parts[rank][0]
         assert graph_local.n == self.n_local
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self.exchange = exchange
+        self.peer: PeerExchange = None
+
+    def close(self) -> None:
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     def _gather(self, local_panel: torch.Tensor, x_full: torch.Tensor) -> None:
         w = x_full.shape[1]
@@ -250,7 +342,10 @@ class RowPartitionedStep:
             out = eng._buf("out", n * S * ld)[: n * S * ld].view(n, S, ld)
             dout = eng._buf("dout", n * S * ld)[: n * S * ld].view(n, S, ld)
             gates = [eng._buf("gate%d" % l, n * S)[: n * S].view(n, S) for l in range(layers)]
-            x_full = eng._buf("x_full", self.n_total * W)[: self.n_total * W].view(self.n_total, W)
+            use_peer = self.exchange == "peer"
+            if use_peer and self.peer is None:
+                self.peer = PeerExchange(self.parts, self.rank, W, dev, self.group)
+            x_full = None if use_peer else eng._buf("x_full", self.n_total * W)[: self.n_total * W].view(self.n_total, W)
             bn_sums = eng._buf("bn_sums", 2 * S * d, dtype=torch.float64)[: 2 * S * d]
             seed, step = model._next_dropout_counter() if model.training else (0, 0)
             bn = model.batch_norm
@@ -261,20 +356,30 @@ class RowPartitionedStep:
                                    bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld,
                                    getattr(model, "gate_off", False))
             m.n_total, m.row_begin = self.n_total, self.parts[self.rank][0]
-            m.x_full, m.bn_sums = x_full.data_ptr(), bn_sums.data_ptr()
+            m.x_full, m.bn_sums = (None if use_peer else x_full.data_ptr()), bn_sums.data_ptr()
             pub = C.c_void_p(0)
+            peer_ref = []                  # keeps the cgcn_peer_panel the struct points at alive
 
             def phase(kind, layer=0):
                 m.stream = _lib.current_stream()
+                if use_peer:
+                    peer_ref[:] = [self.peer.panel()]
+                    m.peer = C.cast(C.pointer(peer_ref[0]), C.c_void_p)
                 _lib.check(lib.cgcn_model_phase(C.byref(m), kind, layer, C.byref(pub)), "cgcn_model_phase(%d,%d)" % (kind, layer))
                 return pub.value
 
             def gather_ptr(ptr):          # the published panel lives in the workspace: wrap it without copying
+                if use_peer:
+                    self.peer.publish(ptr, n * W * 4)
+                    return
                 off = (ptr - ws.data_ptr()) // 4
                 self._gather(ws[off: off + n * W], x_full)
 
             # ---- forward
-            self._gather(panel_local, x_full)
+            if use_peer:
+                self.peer.publish(ops._f32c(panel_local).data_ptr(), n * W * 4)
+            else:
+                self._gather(panel_local, x_full)
             for l in range(layers):
                 p = phase(PHASE_FWD_LAYER, l)
                 if p:

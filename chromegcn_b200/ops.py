@@ -45,6 +45,41 @@ def spmm(graph: HiCGraph, x: torch.Tensor, mean: bool = True, residual: Optional
     return out
 
 
+def peer_panel(blocks: Sequence[int], row_begin: Sequence[int], rank: int) -> _lib.PeerPanel:
+    """`cgcn_peer_panel` over `len(blocks)` exchange buffers given as device addresses."""
+    world = len(blocks)
+    if not 1 <= world <= _lib.MAX_PEERS or len(row_begin) != world + 1:
+        raise _lib.ChromeGCNNativeError("peer_panel: world=%d (max %d)" % (world, _lib.MAX_PEERS))
+    pp = _lib.PeerPanel()
+    pp.world, pp.rank = world, rank
+    for r in range(world):
+        pp.base[r] = int(blocks[r])
+        pp.row_begin[r] = int(row_begin[r])
+    pp.row_begin[world] = int(row_begin[world])
+    return pp
+
+
+def spmm_peer(graph: HiCGraph, blocks: Sequence[torch.Tensor], rank: int, mean: bool = True,
+              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`cgcn_spmm_peer`: `graph` holds the rows of block `rank` with global column indices; `blocks[r]` is the
+    `[rows_r, width]` panel block rank r owns (tensors on this device, or peer-mapped memory)."""
+    lib = _lib.load()
+    blocks = [_f32c(b) for b in blocks]
+    begins = [0]
+    for b in blocks:
+        begins.append(begins[-1] + b.shape[0])
+    width = blocks[rank].numel() // max(blocks[rank].shape[0], 1)
+    if out is None:
+        out = torch.empty(graph.n, width, dtype=torch.float32, device=blocks[rank].device)
+    res = _f32c(residual) if residual is not None else None
+    g = graph.c_struct()
+    pp = peer_panel([b.data_ptr() for b in blocks], begins, rank)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.cgcn_spmm_peer(C.byref(g), C.byref(pp), out.data_ptr(), width, 1 if mean else 0, _lib.ptr(res),
+                                      _lib.current_stream()), "cgcn_spmm_peer")
+    return out
+
+
 def gemm_rowpanel(a: torch.Tensor, b: torch.Tensor, b_transposed: bool = False, bias: Optional[torch.Tensor] = None,
                   rowscale_graph: Optional[HiCGraph] = None, rowscale_group: int = 1, impl: int = GEMM_AUTO,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:

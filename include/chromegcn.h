@@ -39,6 +39,7 @@ extern "C" {
 
 #define CGCN_ABI_VERSION 4
 #define CGCN_MAX_LAYERS 4
+#define CGCN_MAX_PEERS 8    /* GPUs of one NVSwitch box */
 
 typedef void* cgcn_stream_t; /* cudaStream_t */
 
@@ -57,7 +58,7 @@ const char* cgcn_last_error(void);
 /* SM count and compute capability of the current device. */
 int cgcn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* sizeof() of the structs below as compiled, for binding self-checks: which = 0 cgcn_graph,
- * 1 cgcn_params, 2 cgcn_model. */
+ * 1 cgcn_params, 2 cgcn_model, 3 cgcn_peer_panel. */
 size_t cgcn_sizeof(int32_t which);
 /* Number of kernels this library has launched from the calling process (all threads). */
 int64_t cgcn_launch_count(void);
@@ -134,6 +135,38 @@ typedef struct cgcn_graph {
  */
 int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, int32_t scale_mode,
               const float* residual, cgcn_stream_t stream);
+
+/* ------------------------------------- piece 2b: peer-memory SpMM (one graph over several GPUs) ---- */
+/*
+ * One graph row-partitioned over the GPUs of one NVLink / NVSwitch box (BASELINE.json configs[3]; the reference
+ * has no multi-GPU GCN path).  Instead of all-gathering the feature panel before every SpMM, each
+ * rank PUBLISHES its row block into an exchange buffer that the other ranks map into their address space (CUDA
+ * IPC), and the SpMM kernel gathers neighbour rows straight from the owner's HBM with NVLink loads: only the rows
+ * a rank's edges actually touch cross the fabric (Hi-C graphs are near-diagonal, so almost none do), the local
+ * block is read at HBM / L2 speed, and no [n_total][width] copy of the panel exists anywhere.
+ *
+ * Protocol (host): cgcn_peer_alloc on every rank -> exchange the 64-byte handles (any transport) ->
+ * cgcn_peer_open the others -> per exchange step: cgcn_peer_publish (device copy into the own buffer), a
+ * cross-rank barrier ordered on the stream (e.g. a one-element NCCL all-reduce), then cgcn_spmm_peer.  Two
+ * buffers used alternately make one barrier per exchange sufficient.
+ */
+int cgcn_peer_alloc(size_t bytes, void** ptr_host, unsigned char handle_host[64]);  /* cudaMalloc + IPC handle */
+int cgcn_peer_open(const unsigned char handle_host[64], void** ptr_host);           /* map a peer's buffer */
+int cgcn_peer_close(void* ptr);
+int cgcn_peer_free(void* ptr);
+int cgcn_peer_publish(void* exchange_buffer, const void* local_panel, size_t bytes, cgcn_stream_t stream);
+
+typedef struct cgcn_peer_panel {
+  int32_t world;                          /* ranks sharing the graph, <= CGCN_MAX_PEERS */
+  int32_t rank;
+  int32_t row_begin[CGCN_MAX_PEERS + 1];  /* rank r owns global rows [row_begin[r], row_begin[r+1]) */
+  const float* base[CGCN_MAX_PEERS];      /* base[r]: rank r's exchange buffer, row row_begin[r] first */
+} cgcn_peer_panel;
+
+/* cgcn_spmm with the gathered panel spread over the ranks' exchange buffers: g holds the LOCAL rows with GLOBAL
+ * column indices; out / residual are local [g->n][width]. */
+int cgcn_spmm_peer(const cgcn_graph* g, const cgcn_peer_panel* panel, float* out, int32_t width, int32_t scale_mode,
+                   const float* residual, cgcn_stream_t stream);
 
 /* ------------------------------------------------ piece 3: dense contractions ---- */
 /* gemm_impl: 0 = auto (tcgen05 when the shape allows), 1 = fp32 FFMA kernel, 2 = tcgen05 3xTF32. */
@@ -218,6 +251,9 @@ typedef struct cgcn_model {
   int64_t n_total;
   float* x_full;
   double* bn_sums;
+  /* Alternative to x_full: the panel the next SpMM stage gathers from lives in the ranks' exchange buffers
+   * (cgcn_spmm_peer).  NULL = use x_full. */
+  const cgcn_peer_panel* peer;
 } cgcn_model;
 
 size_t cgcn_model_workspace_bytes(int32_t n, int32_t d, int32_t nclass, int32_t layers, int32_t strands);
@@ -235,6 +271,8 @@ int cgcn_model_backward(const cgcn_model* m);
  *   BWD_HEAD ; all-reduce bn_sums ; BWD_LAYER(L-1) ; [all-gather *publish -> x_full ; BWD_LAYER(L-2)] ;
  *   [need_input_grad: all-gather *publish -> x_full ; BWD_INPUT] ; all-reduce the flat gradient buffer.
  * *publish is the local panel to gather before the next stage (NULL if none).
+ * With m->peer set, "all-gather X -> x_full" becomes "cgcn_peer_publish X ; barrier" and the stage's SpMM reads
+ * the peers' exchange buffers directly (no x_full).
  */
 enum { CGCN_PHASE_FWD_LAYER = 0, CGCN_PHASE_FWD_HEAD = 1, CGCN_PHASE_BWD_HEAD = 2, CGCN_PHASE_BWD_LAYER = 3, CGCN_PHASE_BWD_INPUT = 4 };
 int cgcn_model_phase(const cgcn_model* m, int32_t kind, int32_t layer, const float** publish);

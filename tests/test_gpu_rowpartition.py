@@ -44,7 +44,7 @@ def _single_gpu_reference(device, dropout=0.0, input_grad=True):
             m.batch_norm.running_var.clone())
 
 
-def _partitioned(device, rank, world, dropout=0.0, input_grad=True, group=None):
+def _partitioned(device, rank, world, dropout=0.0, input_grad=True, group=None, exchange="nccl"):
     from chromegcn_b200 import dist as cdist
     from chromegcn_b200.graph import HiCGraph
     from chromegcn_b200 import ops
@@ -54,26 +54,56 @@ def _partitioned(device, rank, world, dropout=0.0, input_grad=True, group=None):
     b, e = parts[rank]
     lp, lc = cdist.local_rows_csr(rp, ci, b, e)
     g = HiCGraph.from_csr_pattern(lp, lc, device, add_selfloops=False)
-    step = cdist.RowPartitionedStep(m, g, parts, rank, 2, group)
+    step = cdist.RowPartitionedStep(m, g, parts, rank, 2, group, exchange=exchange)
     panel = ops.interleave_strands([torch.from_numpy(z["x_f"][b:e]).to(device), torch.from_numpy(z["x_r"][b:e]).to(device)])
     loss = torch.zeros(1, device=device)
     xg = torch.empty_like(panel) if input_grad else None
     out, _ = step.run(panel, torch.from_numpy(z["target"][b:e]).to(device), loss, train=True, input_grad=xg)
+    if exchange == "peer":
+        assert step.peer.exchanges == 4          # x_in, layer-1 output, t of layer 2, t of layer 1 (input gradients)
+        out = out.clone()
+        torch.cuda.synchronize(device)
+        step.close()
     return out, loss, {k: p.grad for k, p in m.named_parameters()}, xg, m.batch_norm.running_var, (b, e)
 
 
-def test_phase_api_world1_is_bit_identical():
+@pytest.mark.parametrize("width", [128, 256])
+@pytest.mark.parametrize("mean", [True, False])
+def test_spmm_peer_blocks_on_one_device_match_spmm(width, mean):
+    """The peer-memory SpMM with the panel split into 3 uneven blocks (three separate allocations on one GPU stand
+    in for three ranks' exchange buffers) is bit-identical to the single-panel SpMM on every block's rows."""
+    from chromegcn_b200 import dist as cdist, ops
+    from chromegcn_b200.graph import HiCGraph
+    dev = torch.device("cuda", 0)
+    z = np.load(os.path.join(GOLDEN, "model_l2_stress.npz"))
+    rp, ci = oadj.pattern_with_selfloops(z["indptr"], z["indices"])
+    n = rp.shape[0] - 1
+    gen = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(n, width, device=dev, generator=gen)
+    res = torch.randn(n, width, device=dev, generator=gen)
+    full = ops.spmm(HiCGraph.from_csr_pattern(rp, ci, dev, add_selfloops=False), x, mean=mean, residual=res)
+    cuts = [0, n // 5, n // 5 + n // 2, n]
+    blocks = [x[cuts[r]: cuts[r + 1]].clone() for r in range(3)]
+    for r in range(3):
+        lp, lc = cdist.local_rows_csr(rp, ci, cuts[r], cuts[r + 1])
+        g = HiCGraph.from_csr_pattern(lp, lc, dev, add_selfloops=False)
+        got = ops.spmm_peer(g, blocks, r, mean=mean, residual=res[cuts[r]: cuts[r + 1]])
+        assert torch.equal(got, full[cuts[r]: cuts[r + 1]]), r
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_phase_api_world1_is_bit_identical(exchange):
     dev = torch.device("cuda", 0)
     os.environ["CGCN_NO_SIDE_STREAM"] = "1"      # same stream order in both runs (fixed-order reductions either way)
     ref = _single_gpu_reference(dev)
-    got = _partitioned(dev, 0, 1)
+    got = _partitioned(dev, 0, 1, exchange=exchange)
     assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
     for k in ref[2]:
         assert torch.equal(got[2][k], ref[2][k]), k
     assert torch.equal(got[3], ref[3]) and torch.equal(got[4], ref[4])
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, exchange="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
@@ -82,7 +112,7 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         ref = _single_gpu_reference(dev)
-        out, loss, grads, xg, rv, (b, e) = _partitioned(dev, rank, world)
+        out, loss, grads, xg, rv, (b, e) = _partitioned(dev, rank, world, exchange=exchange)
         errs = {"out": ogcn.max_rel(out.cpu(), ref[0][b:e].cpu()), "loss": abs(loss.item() - ref[1].item()) / abs(ref[1].item()),
                 "xgrad": ogcn.max_rel(xg.cpu(), ref[3][b:e].cpu()), "running_var": ogcn.max_rel(rv.cpu(), ref[4].cpu())}
         for k in ref[2]:
@@ -93,7 +123,8 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_row_partition_two_gpus_matches_single_gpu():
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_row_partition_two_gpus_matches_single_gpu(exchange):
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -101,7 +132,7 @@ def test_row_partition_two_gpus_matches_single_gpu():
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, exchange)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

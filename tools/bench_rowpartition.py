@@ -32,7 +32,8 @@ m = ChromeGCN(128, 128, 103, 0.2, True, 2).to(dev).train()
 if world > 1:
     for p in m.parameters(): dist.broadcast(p.data, 0)
 opt = FlatSGD(m, lr=0.25)
-step = cdist.RowPartitionedStep(m, g, parts, rank, 2)
+exchange = os.environ.get("CGCN_EXCHANGE", "peer")            # "peer": NVLink loads inside the SpMM ; "nccl": all-gather
+step = cdist.RowPartitionedStep(m, g, parts, rank, 2, exchange=exchange)
 gen = torch.Generator(device=dev).manual_seed(100 + rank)
 panel = torch.randn(e - b, 2, 128, device=dev, generator=gen)
 tgt = (torch.rand(e - b, 103, device=dev, generator=gen) < 0.05).float()
@@ -52,5 +53,7 @@ if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"workload": "ST: one chromosome N=%d, %d stored entries, d=128, 2 strands, row-partitioned x%d" % (n, nnz_total, world),
                       "n_gpus": world, "ms_per_step": float(ms.item()), "GE_per_s": nnz_total / float(ms.item()) / 1e6,
-                      "allgather_bytes_per_step_per_rank": 3 * n * 2 * 128 * 4, "loss": float(loss.item() / (warmup + steps))}))
+                      "exchange": exchange,
+                      "allgather_bytes_per_step_per_rank": (3 * n * 2 * 128 * 4) if exchange == "nccl" else 0, "loss": float(loss.item() / (warmup + steps))}))
+step.close()
 if world > 1: dist.destroy_process_group()
