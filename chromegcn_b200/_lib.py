@@ -11,7 +11,7 @@ from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libchromegcn.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LAYERS = 4
 MAX_PEERS = 8
 
@@ -85,7 +85,9 @@ PROTOTYPES = {
     "cgcn_bce_workspace_bytes": (_SZ, [_I32, _I32]),
     "cgcn_bce_loss": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "cgcn_model_phase": (C.c_int, [C.POINTER(Model), _I32, _I32, C.POINTER(_P)]),
+    "cgcn_bce_loss_bits": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "cgcn_train_step": (C.c_int, [C.POINTER(Model), _P, _P, _P, _P]),
+    "cgcn_train_step_bits": (C.c_int, [C.POINTER(Model), _P, _P, _P, _P]),
     "cgcn_sgd_step": (C.c_int, [_P, _P, _P, _I64, _F32, _F32, _F32, _F32, _P]),
     "cgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _I64, _F32, _P]),
     "cgcn_interleave_strands": (C.c_int, [C.POINTER(_P), _I32, _I32, _I32, _P, _P]),

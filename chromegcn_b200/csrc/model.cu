@@ -38,8 +38,8 @@ size_t tc_workspace_bytes();
 
 int rowwise_max_grid();
 int bce_grid();
-int bce_launch(const float* out, const float* target, int n, int C, int S, int ld, float* probs, float* loss_sum,
-               float* out_grad, float* partial, int64_t n_total, cudaStream_t stream);
+int bce_launch(const float* out, const float* target, const uint32_t* target_bits, int n, int C, int S, int ld, float* probs,
+               float* loss_sum, float* out_grad, float* partial, int64_t n_total, cudaStream_t stream);
 int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* dst, float* partial, cudaStream_t stream);
 int bn_finalize_launch(const float* partial, int parts, int64_t n, int S, int D, float eps, float momentum, int training,
                        float* running_mean, float* running_var, int64_t* nbt, float* mean_out, float* rstd_out,
@@ -604,16 +604,26 @@ extern "C" int cgcn_model_phase(const cgcn_model* m, int32_t kind, int32_t layer
 }
 extern "C" int cgcn_model_backward(const cgcn_model* m) { return model_backward(m); }
 
-extern "C" int cgcn_train_step(const cgcn_model* m, const float* target, float* probs, float* loss_sum_out,
-                               float* out_grad_scratch) {
-  CGCN_REQUIRE(m && target && loss_sum_out && out_grad_scratch, "cgcn_train_step: null argument");
+static int train_step(const cgcn_model* m, const float* target, const uint32_t* target_bits, float* probs, float* loss_sum_out,
+                      float* out_grad_scratch) {
+  CGCN_REQUIRE(m && (target || target_bits) && loss_sum_out && out_grad_scratch, "cgcn_train_step: null argument");
   CGCN_TRY(model_forward(m));
   const WsLayout lay = make_layout(m->graph.n, m->d, m->nclass, m->layers, m->strands);
-  CGCN_TRY(bce_launch(m->out, target, m->graph.n, m->nclass, m->strands, m->out_ld > 0 ? m->out_ld : m->nclass, probs,
+  CGCN_TRY(bce_launch(m->out, target, target_bits, m->graph.n, m->nclass, m->strands, m->out_ld > 0 ? m->out_ld : m->nclass, probs,
                       loss_sum_out, out_grad_scratch, m->workspace + lay.partial, 0, static_cast<cudaStream_t>(m->stream)));
   cgcn_model mb = *m;
   mb.out_grad = out_grad_scratch;
   return model_backward(&mb);
+}
+
+extern "C" int cgcn_train_step(const cgcn_model* m, const float* target, float* probs, float* loss_sum_out,
+                               float* out_grad_scratch) {
+  return train_step(m, target, nullptr, probs, loss_sum_out, out_grad_scratch);
+}
+
+extern "C" int cgcn_train_step_bits(const cgcn_model* m, const uint32_t* target_bits, float* probs, float* loss_sum_out,
+                                    float* out_grad_scratch) {
+  return train_step(m, nullptr, target_bits, probs, loss_sum_out, out_grad_scratch);
 }
 
 extern "C" int cgcn_gemm_rowpanel(const float* A, int64_t lda, const float* B, int32_t b_transposed, const float* bias,

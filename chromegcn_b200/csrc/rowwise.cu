@@ -522,7 +522,8 @@ __global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __rest
 // ------------------------------------------------------------------------------ BCE-with-logits
 struct BceArgs {
   const float* out;    // [n][S][C]
-  const float* target; // [n][C]
+  const float* target; // [n][C], or NULL when target_bits is set
+  const uint32_t* target_bits;   // [n][(C+31)/32] little-endian bit rows (bit c of a row = label c), or NULL
   float* probs;        // [n][C] or NULL
   float* out_grad;     // [n][S][C] or NULL
   float* partial;      // [grid]
@@ -539,6 +540,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
   const float inv_s = 1.0f / S;
   const uint32_t total = static_cast<uint32_t>(a.total), C = static_cast<uint32_t>(a.C);
   const uint32_t LD = static_cast<uint32_t>(a.ld);
+  const uint32_t WPR = (C + 31u) >> 5;                           // words per bit-packed target row
   // flat over the n x ld elements (padding columns only get a zero gradient), 4 independent elements per
   // thread per trip (coalesced, 32-bit index math)
   for (uint32_t e0 = blockIdx.x * 1024u + threadIdx.x; e0 < total; e0 += gridDim.x * 1024u) {
@@ -558,7 +560,9 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
           float ps[SS];
 #pragma unroll
           for (uint32_t s = 0; s < S; ++s) ps[s] = __ldg(a.out + ob[u] + s * LD);
-          t[u] = __ldg(a.target + rr[u] * C + cc[u]);
+          t[u] = (a.target_bits != nullptr)
+                     ? static_cast<float>((__ldg(a.target_bits + rr[u] * WPR + (cc[u] >> 5)) >> (cc[u] & 31u)) & 1u)
+                     : __ldg(a.target + rr[u] * C + cc[u]);
 #pragma unroll
           for (uint32_t s = 0; s < S; ++s) p[u] += ps[s];
         }
@@ -814,10 +818,10 @@ int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* dst, fl
 
 int bce_grid() { return sm_count() * 8; }
 
-int bce_launch(const float* out, const float* target, int n, int C, int S, int ld, float* probs, float* loss_sum,
-               float* out_grad, float* partial, int64_t n_total, cudaStream_t stream) {
+int bce_launch(const float* out, const float* target, const uint32_t* target_bits, int n, int C, int S, int ld, float* probs,
+               float* loss_sum, float* out_grad, float* partial, int64_t n_total, cudaStream_t stream) {
   if (n_total <= 0) n_total = n;                       // row-partitioned graphs normalise by the global row count
-  BceArgs a{out, target, probs, out_grad, partial, static_cast<int64_t>(n) * ld, C, S, ld,
+  BceArgs a{out, target, target_bits, probs, out_grad, partial, static_cast<int64_t>(n) * ld, C, S, ld,
             static_cast<float>(1.0 / (static_cast<double>(n_total) * C))};
   CGCN_REQUIRE(a.total * S < 4294967296LL, "cgcn_bce_loss: n * nclass * strands must fit 32 bits");
   int grid = static_cast<int>((a.total + 1023) / 1024);
@@ -851,7 +855,22 @@ extern "C" int cgcn_bce_loss(const float* out, const float* target, int32_t n, i
     set_error("cgcn_bce_loss: workspace too small");
     return CGCN_ERR_WORKSPACE;
   }
-  return bce_launch(out, target, n, nclass, strands, out_ld, probs, loss_sum_out, out_grad,
+  return bce_launch(out, target, nullptr, n, nclass, strands, out_ld, probs, loss_sum_out, out_grad,
+                    static_cast<float*>(workspace), n_total, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cgcn_bce_loss_bits(const float* out, const uint32_t* target_bits, int32_t n, int32_t nclass, int32_t strands,
+                                  int32_t out_ld, int64_t n_total, float* probs, float* loss_sum_out, float* out_grad,
+                                  void* workspace, size_t workspace_bytes, cgcn_stream_t stream) {
+  CGCN_REQUIRE(out && target_bits && loss_sum_out, "cgcn_bce_loss_bits: null argument");
+  CGCN_REQUIRE(n >= 1 && nclass >= 1 && (strands == 1 || strands == 2), "cgcn_bce_loss_bits: bad shape");
+  if (out_ld <= 0) out_ld = nclass;
+  CGCN_REQUIRE(out_ld >= nclass, "cgcn_bce_loss_bits: out_ld %d < nclass %d", out_ld, nclass);
+  if (workspace == nullptr || workspace_bytes < cgcn_bce_workspace_bytes(n, nclass)) {
+    set_error("cgcn_bce_loss_bits: workspace too small");
+    return CGCN_ERR_WORKSPACE;
+  }
+  return bce_launch(out, nullptr, target_bits, n, nclass, strands, out_ld, probs, loss_sum_out, out_grad,
                     static_cast<float*>(workspace), n_total, static_cast<cudaStream_t>(stream));
 }
 

@@ -160,16 +160,24 @@ class ChromosomeEngine:
                                    panel, input_grad, out, gates, None, ws, model.gemm_impl,
                                    bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld,
                                    getattr(model, "gate_off", False))
-            tgt = ops._f32c(target)
+            bits = target.dtype == torch.int32            # ops.pack_targets bit rows
+            if bits:
+                if target.shape != (n, (nclass + 31) // 32):
+                    raise ValueError("bit-packed targets must be [n, ceil(nclass/32)] int32")
+                tgt = target.contiguous()
+            else:
+                tgt = ops._f32c(target)
             if train:
-                _lib.check(lib.cgcn_train_step(C.byref(m), tgt.data_ptr(), _lib.ptr(probs_out), loss_slot.data_ptr(),
-                                               dout.data_ptr()), "cgcn_train_step")
+                step_fn = lib.cgcn_train_step_bits if bits else lib.cgcn_train_step
+                _lib.check(step_fn(C.byref(m), tgt.data_ptr(), _lib.ptr(probs_out), loss_slot.data_ptr(),
+                                   dout.data_ptr()), "cgcn_train_step")
                 fp.attach_grads()
             else:
                 _lib.check(lib.cgcn_model_forward(C.byref(m)), "cgcn_model_forward")
                 bce_ws = self._buf("bce_ws", lib.cgcn_bce_workspace_bytes(n, nclass) // 4 + 64)
-                _lib.check(lib.cgcn_bce_loss(out.data_ptr(), tgt.data_ptr(), n, nclass, S, ld, 0, _lib.ptr(probs_out),
-                                             loss_slot.data_ptr(), None, bce_ws.data_ptr(), bce_ws.numel() * 4,
-                                             _lib.current_stream()), "cgcn_bce_loss")
+                loss_fn = lib.cgcn_bce_loss_bits if bits else lib.cgcn_bce_loss
+                _lib.check(loss_fn(out.data_ptr(), tgt.data_ptr(), n, nclass, S, ld, 0, _lib.ptr(probs_out),
+                                   loss_slot.data_ptr(), None, bce_ws.data_ptr(), bce_ws.numel() * 4,
+                                   _lib.current_stream()), "cgcn_bce_loss")
         self.step_count += 1
         return out[:, :, :nclass], gates

@@ -5,7 +5,9 @@ per chromosome per epoch on the host -- unpickle the graphs, scipy `process_grap
 H2D copies, `loss.item()`, `.cpu()` + quadratic `torch.cat` -- becomes:
   * graph pickles are read once and the `bin(A+I)` patterns stay on the GPU (cache keyed by file);
   * features / targets stream host -> device on a copy stream, one chromosome ahead of the compute
-    stream (or stay resident when `opt.cache_features_on_device` is set);
+    stream (or stay resident when `opt.cache_features_on_device` is set); the 0/1 label matrix, the one
+    input that never changes between epochs, is bit-packed on the host the first time it is seen
+    (pinned, 16 B per window instead of 4*nclass) and consumed in that form by `cgcn_train_step_bits`;
   * the chromosome step is one `cgcn_train_step` call; losses go to a device array, probabilities
     into one preallocated `[sum N, nclass]` device buffer; one D2H copy and one sync per split.
 """
@@ -32,6 +34,9 @@ def clear_caches() -> None:
     _GRAPHS.clear()
     _ENGINES.clear()
     _RESIDENT.clear()
+    _TARGETS.clear()
+    _STAGING.clear()
+    _PACKED.clear()
 
 
 def engine_for(model) -> ChromosomeEngine:
@@ -74,15 +79,38 @@ _TARGETS: Dict = {}          # (id(dict), data_ptrs) -> concatenated CPU targets
 _STAGING: Dict = {}          # (device, slot) -> persistent device staging buffers of the H2D pipeline
 
 
-def _staging(device, slot: int, n: int, d: int, nclass: int):
-    key = (str(device), slot)
+def _staging(device, slot: int, n: int, d: int, nclass: int, bits: bool):
+    """Device staging buffers of pipeline slot `slot`: x_f, x_r and the targets (float `[n, nclass]`, or int32 bit
+    rows `[n, ceil(nclass/32)]`)."""
+    tcols, tdtype = ((nclass + 31) // 32, torch.int32) if bits else (nclass, torch.float32)
+    key = (str(device), slot, bits)
     cur = _STAGING.get(key)
-    if cur is None or cur[0].shape[0] < n or cur[0].shape[1] != d or cur[2].shape[1] != nclass:
+    if cur is None or cur[0].shape[0] < n or cur[0].shape[1] != d or cur[2].shape[1] != tcols:
         rows = max(n, cur[0].shape[0] if cur is not None and cur[0].shape[1] == d else 0)
         cur = (torch.empty(rows, d, dtype=torch.float32, device=device), torch.empty(rows, d, dtype=torch.float32, device=device),
-               torch.empty(rows, nclass, dtype=torch.float32, device=device))
+               torch.empty(rows, tcols, dtype=tdtype, device=device))
         _STAGING[key] = cur
     return cur[0][:n], cur[1][:n], cur[2][:n]
+
+
+_PACKED: Dict = {}           # id(target tensor) -> (weakref, version, pinned int32 bit rows | None for soft labels)
+
+
+def packed_target(target: torch.Tensor):
+    """The bit-packed pinned copy of a chromosome's 0/1 label matrix, built the first time the tensor is seen
+    (`None` for soft labels, which keep the float path).  The entry is tied to the tensor object (weak reference)
+    and its in-place version counter, so a recycled address or an edited matrix is packed again."""
+    import weakref
+    hit = _PACKED.get(id(target))
+    if hit is not None and hit[0]() is target and hit[1] == target._version:
+        return hit[2]
+    from . import ops
+    packed = ops.pack_targets(target, pin=True)
+    if len(_PACKED) > 256:
+        for k in [k for k, v in _PACKED.items() if v[0]() is None]:
+            del _PACKED[k]
+    _PACKED[id(target)] = (weakref.ref(target), target._version, packed)
+    return packed
 
 
 def _all_targets(chrom_feature_dict, chroms):
@@ -110,6 +138,7 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
     nclass = ChromeModel.out.out_features
     graphs = graphs_for(opt, split, chroms, sizes, device)
     resident = bool(getattr(opt, "cache_features_on_device", False))
+    pack_labels = bool(getattr(opt, "pack_labels", True))
 
     total_rows = sum(sizes.values())
     main = torch.cuda.current_stream(device)
@@ -133,13 +162,14 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
                 staged[k % 2] = ("resident",) + _RESIDENT[rkey]
                 return
             n, d = feats["forward"].shape
-            x_f, x_r, tgt = _staging(device, k % 2, n, d, nclass)
+            tgt_host = None if (resident or not pack_labels) else packed_target(feats["target"])
+            x_f, x_r, tgt = _staging(device, k % 2, n, d, nclass, tgt_host is not None)
             with torch.cuda.stream(h2d):
                 if k >= 2:
                     h2d.wait_event(consumed[k % 2])          # the slot's previous tenant has been packed / consumed
                 x_f.copy_(feats["forward"], non_blocking=True)
                 x_r.copy_(feats["backward"], non_blocking=True)
-                tgt.copy_(feats["target"], non_blocking=True)
+                tgt.copy_(feats["target"] if tgt_host is None else tgt_host, non_blocking=True)
                 ready[k % 2].record(h2d)
             staged[k % 2] = ("fresh", x_f, x_r, tgt)
 

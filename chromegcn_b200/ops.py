@@ -121,14 +121,46 @@ def gemm_gram(a: torch.Tensor, b: torch.Tensor, impl: int = GEMM_AUTO, out: Opti
     return out
 
 
+def pack_targets(target: torch.Tensor, pin: bool = False) -> Optional[torch.Tensor]:
+    """Host side of `cgcn_bce_loss_bits` / `cgcn_train_step_bits`: a 0/1 label matrix `[n, C]` (finetune.py:32)
+    as `[n, ceil(C/32)]` int32 bit rows (bit c of a row = label c).  Returns None when some entry is neither
+    0 nor 1 (soft labels keep the float path)."""
+    import numpy as np
+    t = target.detach().cpu().numpy()
+    b = t != 0
+    if not np.array_equal(b.astype(t.dtype), t):
+        return None
+    n, c = b.shape
+    wpr = (c + 31) // 32
+    packed = np.zeros((n, wpr * 4), dtype=np.uint8)
+    packed[:, : (c + 7) // 8] = np.packbits(b, axis=1, bitorder="little")
+    out = torch.from_numpy(packed.view("<i4").reshape(n, wpr))
+    return out.pin_memory() if pin else out
+
+
 def bce_loss(out: torch.Tensor, target: torch.Tensor, strands: int, loss_acc: torch.Tensor,
-             want_probs: bool = True, want_grad: bool = True, n_total: int = 0):
+             want_probs: bool = True, want_grad: bool = True, n_total: int = 0, nclass: Optional[int] = None):
     """finetune.py:43-45,52 on `[n, strands, C]` logits: returns `(probs [n, C] | None, out_grad | None)`
-    and adds the mean loss to `loss_acc[0]`."""
+    and adds the mean loss to `loss_acc[0]`.  An int32 `target` is a `pack_targets` bit matrix (pass `nclass`)."""
     lib = _lib.load()
-    out, target = _f32c(out), _f32c(target)
-    n, c = target.shape
+    out = _f32c(out)
     ld = out.shape[-1]                       # row pitch of the logits (>= nclass)
+    if target.dtype == torch.int32:
+        if nclass is None or target.shape[1] != (nclass + 31) // 32:
+            raise ValueError("bit-packed targets need nclass with ceil(nclass/32) == target.shape[1]")
+        target = target.contiguous()
+        n, c = target.shape[0], int(nclass)
+        probs = torch.empty(n, c, dtype=torch.float32, device=out.device) if want_probs else None
+        grad = torch.empty_like(out) if want_grad else None
+        with torch.cuda.device(out.device):
+            need = lib.cgcn_bce_workspace_bytes(n, c)
+            ws = torch.empty(need, dtype=torch.uint8, device=out.device)
+            _lib.check(lib.cgcn_bce_loss_bits(out.data_ptr(), target.data_ptr(), n, c, strands, ld, n_total, _lib.ptr(probs),
+                                              loss_acc.data_ptr(), _lib.ptr(grad), ws.data_ptr(), need,
+                                              _lib.current_stream()), "cgcn_bce_loss_bits")
+        return probs, grad
+    target = _f32c(target)
+    n, c = target.shape
     probs = torch.empty(n, c, dtype=torch.float32, device=out.device) if want_probs else None
     grad = torch.empty_like(out) if want_grad else None
     with torch.cuda.device(out.device):

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CGCN_ABI_VERSION 4
+#define CGCN_ABI_VERSION 5
 #define CGCN_MAX_LAYERS 4
 #define CGCN_MAX_PEERS 8    /* GPUs of one NVSwitch box */
 
@@ -288,11 +288,20 @@ int cgcn_bce_loss(const float* out, const float* target, int32_t n, int32_t ncla
                   int64_t n_total /* rows the mean runs over; 0 = n (row-partitioned graphs pass the global count) */,
                   float* probs, float* loss_sum_out, float* out_grad,
                   void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
+/* Same with bit-packed labels: target_bits [n][(nclass+31)/32] uint32, bit (c & 31) of word c >> 5 of a row
+ * = label c (numpy packbits, bitorder 'little').  The label matrix of finetune.py:32 is 0/1 and is the one
+ * input that does not change between epochs, so the host packs it once and each pass moves 1/26 of the
+ * float matrix over PCIe. */
+int cgcn_bce_loss_bits(const float* out, const uint32_t* target_bits, int32_t n, int32_t nclass, int32_t strands,
+                       int32_t out_ld, int64_t n_total, float* probs, float* loss_sum_out, float* out_grad,
+                       void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
 
 /* One iteration of the chromosome loop of finetune.py:39-53 for split == 'train':
  * forward (both strands), loss, backward.  The optimiser step is cgcn_sgd_step / cgcn_adam_step. */
 int cgcn_train_step(const cgcn_model* m, const float* target, float* probs, float* loss_sum_out,
                     float* out_grad_scratch);
+int cgcn_train_step_bits(const cgcn_model* m, const uint32_t* target_bits, float* probs, float* loss_sum_out,
+                         float* out_grad_scratch);
 
 /* ------------------------------------------------------------- optimiser ---- */
 /* torch.optim.SGD(lr, momentum, weight_decay) as built by utils/util_methods.py:18-19, over one flat

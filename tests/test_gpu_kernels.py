@@ -140,6 +140,27 @@ def test_bce_loss_and_gradient():
     assert abs(acc.item() - 2 * loss.item()) <= 4e-6 * abs(loss.item())
 
 
+@pytest.mark.parametrize("c", [103, 1, 32, 33, 128, 200])
+def test_bce_loss_bit_packed_labels_identical_to_float(c):
+    """`cgcn_bce_loss_bits` (labels as bit rows) must reproduce `cgcn_bce_loss` bit for bit."""
+    from chromegcn_b200 import ops
+    gen = torch.Generator().manual_seed(20 + c)
+    n, s = 777, 2
+    ld = (c + 3) // 4 * 4
+    out = torch.zeros(n, s, ld)
+    out[:, :, :c] = torch.randn(n, s, c, generator=gen) * 3
+    tgt = (torch.rand(n, c, generator=gen) < 0.3).float()
+    bits = ops.pack_targets(tgt)
+    assert bits is not None and bits.dtype == torch.int32 and tuple(bits.shape) == (n, (c + 31) // 32)
+    a0, a1 = torch.zeros(1, device=_dev()), torch.zeros(1, device=_dev())
+    p0, g0 = ops.bce_loss(out.to(_dev()), tgt.to(_dev()), s, a0)
+    p1, g1 = ops.bce_loss(out.to(_dev()), bits.to(_dev()), s, a1, nclass=c)
+    assert torch.equal(p0, p1) and torch.equal(g0, g1) and a0.item() == a1.item()
+    soft = tgt.clone()
+    soft[3, 0] = 0.5
+    assert ops.pack_targets(soft) is None                      # soft labels keep the float path
+
+
 @pytest.mark.parametrize("kind", ["sgd", "adam"])
 def test_optimizer_kernels_match_torch(kind):
     from chromegcn_b200 import ops

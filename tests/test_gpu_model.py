@@ -321,6 +321,54 @@ def test_finetune_matches_reference(tmp_path, optim_kind, gemm_impl):
         close(v.float().cpu(), z["sd3." + k], o64.state_dict()[k], "state_dict " + k)
 
 
+def test_finetune_bit_packed_labels_identical_to_float_labels(tmp_path):
+    """finetune() moves the 0/1 label matrix host -> device as bit rows (cgcn_train_step_bits / cgcn_bce_loss_bits);
+    `opt.pack_labels = False` keeps the float matrix of finetune.py:32.  Same kernels, same order of operations:
+    predictions, losses and the trained weights must be bit-identical.  Soft labels fall back to the float path."""
+    import argparse
+    import pickle
+    from scipy import sparse
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200 import finetune as ft
+    from chromegcn_b200.optim import get_optimizer
+    z = np.load(os.path.join(GOLDEN, "finetune.npz"))
+    nclass = int(z["nclass"])
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0.")}
+    graphs = {}
+    for c in ("chr1", "chr2"):
+        ip, ix = z[c + ".indptr"], z[c + ".indices"]
+        graphs[c] = sparse.csr_matrix((np.ones(ix.shape[0]), ix, ip), shape=(ip.shape[0] - 1,) * 2)
+    for split in ("train", "valid"):
+        with open(tmp_path / ("%s_graphs_1200_SQRTVCnorm.pkl" % split), "wb") as fp:
+            pickle.dump(graphs, fp)
+    feats = {c: {k: torch.from_numpy(z["%s.%s" % (c, k)]) for k in ("forward", "backward", "target")} for c in ("chr1", "chr2")}
+    assert all(ft.packed_target(f["target"]) is not None for f in feats.values())
+    results = []
+    for pack in (True, False):
+        ft.clear_caches()
+        torch.manual_seed(7)                                   # the dropout stream's seed is drawn from torch's generator
+        m = ChromeGCN(128, 128, nclass, 0.2, True, 2)
+        m.load_state_dict(sd)
+        m = m.to(_dev())
+        opt = argparse.Namespace(adj_type="hic", graph_root=str(tmp_path), hicsize="1200", hicnorm="SQRTVC", optim="sgd", lr=0.25,
+                                 pack_labels=pack)
+        optimizer = get_optimizer(m, opt)
+        run = []
+        for epoch in (1, 2):
+            p, t, l = ft.finetune(None, m, feats, None, optimizer, epoch, None, opt, "train")
+            pv, _, lv = ft.finetune(None, m, feats, None, optimizer, epoch, None, opt, "valid")
+            run += [p.clone(), torch.tensor(l), pv.clone(), torch.tensor(lv)]
+        run += [v.detach().cpu().clone() for v in m.state_dict().values()]
+        results.append(run)
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
+    soft = {c: dict(f) for c, f in feats.items()}
+    soft["chr1"]["target"] = soft["chr1"]["target"] * 0.75
+    assert ft.packed_target(soft["chr1"]["target"]) is None
+    p, _, l = ft.finetune(None, m, soft, None, optimizer, 3, None, opt, "valid")
+    assert np.isfinite(l) and torch.isfinite(p).all()
+
+
 @pytest.mark.parametrize("gemm_impl", [0, 1])
 def test_eval_from_reference_weights_auroc_aupr(gemm_impl):
     """The reference's trained weights (state_dict after its own 3 epochs) evaluated on the CUDA path:

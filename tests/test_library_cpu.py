@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_abi_version_and_struct_layout(lib):
     import ctypes as C
     from chromegcn_b200 import _lib
-    assert lib.cgcn_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.cgcn_abi_version() == _lib.ABI_VERSION == 5
     assert lib.cgcn_sizeof(0) == C.sizeof(_lib.Graph)
     assert lib.cgcn_sizeof(1) == C.sizeof(_lib.Params)
     assert lib.cgcn_sizeof(2) == C.sizeof(_lib.Model)
@@ -94,3 +94,22 @@ def test_cli_flags_match_reference():
     assert opt.graph_root == "/data/GM12878/1000/hic" and opt.batch_size == 512 and opt.hicsize == "500000"
     assert opt.model_name.endswith(".finetune.lr2_002.gcndrop_20.adam.gcn.layers_2.gate.adj_hic.norm_SQRTVC")
     assert opt.model_name.startswith("/res/GM12878/graph.expecto.128.bsz_64.loss_ce.sgd.lr_25.drop_10_10")
+
+
+def test_pack_targets_bit_layout():
+    """Host side of cgcn_*_bits: bit c of row r == label (r, c); soft labels are refused."""
+    import numpy as np
+    import torch
+    from chromegcn_b200 import ops
+    rng = np.random.default_rng(0)
+    for c in (1, 31, 32, 33, 103, 128, 200):
+        t = (rng.random((50, c)) < 0.4).astype(np.float32)
+        b = ops.pack_targets(torch.from_numpy(t))
+        assert b.dtype == torch.int32 and tuple(b.shape) == (50, (c + 31) // 32)
+        w = b.numpy().view(np.uint32)
+        back = ((w[:, np.arange(c) >> 5] >> (np.arange(c) & 31).astype(np.uint32)) & 1).astype(np.float32)
+        assert np.array_equal(back, t)
+        if c % 32:
+            assert not (w[:, -1] >> np.uint32(c % 32)).any()       # padding bits stay clear
+    t[0, 0] = 0.25
+    assert ops.pack_targets(torch.from_numpy(t)) is None
