@@ -49,6 +49,33 @@ inline int check_launch(const char* what) {
 
 int sm_count();                       // cached, current device
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// One chromosome step is ~34 kernels of 5..60 us each on one stream: the drain / launch / ramp-up bubble between
+// two dependent kernels is a measurable share of it.  Every kernel of the model path starts with pdl_grid_sync()
+// (griddepcontrol.wait: the whole previous grid has completed and its writes are visible; then
+// griddepcontrol.launch_dependents: the next kernel's CTAs may be scheduled as soon as all of this grid's CTAs have
+// started) and is launched through launch_k() with cudaLaunchAttributeProgrammaticStreamSerialization, so the next
+// kernel's launch latency and prologue (barrier init, TMEM allocation, argument fetch) overlap this kernel's tail.
+// Nothing that touches global memory may precede pdl_grid_sync().  CGCN_NO_PDL=1 turns the attribute off.
+bool pdl_enabled();
+void pdl_plain_next(cudaStream_t stream);   // the next launch_k on `stream` is an ordinary launch (after event waits)
+bool pdl_take_plain(cudaStream_t stream);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && !pdl_take_plain(stream)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // one weight operand of a tcgen05 row-panel contraction, to be split (hi/lo TF32) and swizzled into `img`
 struct TcImageSpec {
   const float* B;
@@ -75,6 +102,11 @@ struct Arena {
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

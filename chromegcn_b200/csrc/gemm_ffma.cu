@@ -44,6 +44,7 @@ __device__ __forceinline__ void fma_8x8(float (&acc)[8][8], const float4 a0, con
 }
 
 __global__ void __launch_bounds__(GTHREADS, 2) gemm_rowpanel_kernel(const RowPanelArgs p) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) float smem[];
   float* Bs = smem;                       // [k_pad][GB]
   const int k_pad = (p.k + GBK - 1) / GBK * GBK;
@@ -192,7 +193,7 @@ int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transp
   }
   const int64_t tiles = (m + GB - 1) / GB;
   const int grid = static_cast<int>(tiles < 2LL * sm_count() ? tiles : 2LL * sm_count());
-  gemm_rowpanel_kernel<<<grid, GTHREADS, smem, stream>>>(p);
+  CGCN_CUDA(launch_k(gemm_rowpanel_kernel, dim3(grid), dim3(GTHREADS), smem, stream, p));
   return check_launch("gemm_rowpanel_kernel");
 }
 
@@ -212,6 +213,7 @@ struct GramArgs {
 };
 
 __global__ void __launch_bounds__(GTHREADS, 2) gemm_gram_kernel(const GramArgs p) {
+  pdl_grid_sync();
   __shared__ __align__(16) float As[2][GBK][GB];
   __shared__ __align__(16) float Bs[2][GBK][GB];
   const int tid = threadIdx.x;
@@ -302,6 +304,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_gram_kernel(const GramArgs p
 __global__ void __launch_bounds__(512) gram_finalize_kernel(const float* __restrict__ partial, int parts, int part_stride,
                                                             int pld, int ka, int nb, float* __restrict__ C, int64_t ldc,
                                                             int accumulate) {
+  pdl_grid_sync();
   __shared__ double sh[8][64];
   const int idx = blockIdx.x * 64 + threadIdx.x;
   const int count = ka * nb;
@@ -331,8 +334,8 @@ __global__ void __launch_bounds__(512) gram_finalize_kernel(const float* __restr
 
 void gram_finalize_launch(const float* partial, int parts, int part_stride, int pld, int ka, int nb, float* C,
                           int64_t ldc, int accumulate, cudaStream_t stream) {
-  gram_finalize_kernel<<<(ka * nb + 63) / 64, dim3(64, 8), 0, stream>>>(partial, parts, part_stride, pld, ka, nb, C, ldc,
-                                                                        accumulate);
+  launch_k(gram_finalize_kernel, dim3((ka * nb + 63) / 64), dim3(64, 8), 0, stream, partial, parts, part_stride, pld, ka, nb, C, ldc,
+           accumulate);
 }
 
 int64_t gram_rows_per_cta(int64_t m) {
@@ -362,7 +365,7 @@ int gemm_gram_ffma(const float* A, int64_t lda, const float* B, int64_t ldb, flo
   p.a_vec = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
   p.b_vec = (ldb % 4 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0);
   const int parts = static_cast<int>((m + p.rows_per_cta - 1) / p.rows_per_cta);
-  gemm_gram_kernel<<<parts, GTHREADS, 0, stream>>>(p);
+  CGCN_CUDA(launch_k(gemm_gram_kernel, dim3(parts), dim3(GTHREADS), 0, stream, p));
   CGCN_TRY(check_launch("gemm_gram_kernel"));
   gram_finalize_launch(p.partial, parts, ka * nb, nb, ka, nb, C, ldc, accumulate, stream);
   return check_launch("gram_finalize_kernel");

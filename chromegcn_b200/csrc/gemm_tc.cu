@@ -189,6 +189,7 @@ __device__ __forceinline__ void store_block_coalesced(uint32_t stg, const uint4 
 // that multiplies A[:,k] into C[:,n].
 __global__ void tc_prep_b_kernel(const float* __restrict__ B, int b_transposed, int n_valid, int k_valid,
                                  uint32_t* __restrict__ img) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= TILE * TILE) return;
   const int n = idx >> 7, k = idx & 127;
@@ -212,6 +213,7 @@ struct PrepBatchArgs {
   int b_transposed[PREP_MAX], n_valid[PREP_MAX], k_valid[PREP_MAX];
 };
 __global__ void tc_prep_b_batch_kernel(const PrepBatchArgs a) {
+  pdl_grid_sync();
   const int w = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= TILE * TILE) return;
@@ -273,12 +275,29 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
   const int64_t r_end = r_begin + p.rows_per_cta < p.m ? r_begin + p.rows_per_cta : p.m;
   const int ntile = r_end > r_begin ? static_cast<int>((r_end - r_begin + TILE - 1) / TILE) : 0;
 
+  // Set-up that touches no global memory (barriers, TMEM allocation) runs before the grid dependency resolves, i.e.
+  // while the previous kernel of the stream is still draining (programmatic dependent launch).
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RP_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, NUM_PROD_WARPS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, NUM_EPI_WARPS);
+    }
+    mbar_init(bar_b, 1);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(s_tmem_ptr, 256);
+  pdl_grid_sync();
+
   if (threadIdx.x < TILE)
     reinterpret_cast<float*>(gen + (sBias - base))[threadIdx.x] =
         (p.bias != nullptr && static_cast<int>(threadIdx.x) < p.n_valid) ? __ldg(p.bias + threadIdx.x) : 0.f;
 
-  // Producers put their first tile's loads in flight before anything else: the B image copy, barrier init and
-  // TMEM allocation below then overlap with the DRAM latency of the first A tile.
+  // Producers put their first tile's loads in flight first: the B image copy below then overlaps with the DRAM
+  // latency of the first A tile.
   const int pt = static_cast<int>(threadIdx.x) - (MMA_WARP + 1) * 32;      // 0..255 for producer threads
   float4 v[4][4];      // register ring: one whole tile (4 k-chunks x 4 float4) of look-ahead = 64 KB in flight per SM
   auto issue = [&](int t, int kc) {
@@ -297,25 +316,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
     for (int kc = 0; kc < 4; ++kc) issue(0, kc);
   }
 
-  // Barriers, then the B image (already swizzled by tc_prep_b_kernel) as 8 x 16 KB bulk copies that complete on
-  // bar_b: nothing but the first MMA waits for them.
+  // The B image (already swizzled by tc_prep_b_kernel) as 8 x 16 KB bulk copies that complete on bar_b: nothing but
+  // the first MMA waits for them.
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RP_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, NUM_PROD_WARPS);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, NUM_EPI_WARPS);
-    }
-    mbar_init(bar_b, 1);
-    fence_barrier_init();
     mbar_expect_tx(bar_b, RP_B_BYTES);
 #pragma unroll 1
     for (int i = 0; i < RP_B_BYTES / CHUNK_BYTES; ++i)
       bulk_g2s(sB + i * CHUNK_BYTES, reinterpret_cast<const uint8_t*>(p.b_img) + i * CHUNK_BYTES, CHUNK_BYTES, bar_b);
   }
-  if (warp == MMA_WARP) tmem_alloc(s_tmem_ptr, 256);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -477,6 +485,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcAr
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(s_tmem_ptr, 128);
+  pdl_grid_sync();                   // nothing above touches global memory
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -617,7 +626,7 @@ int tc_prep_images(const TcImageSpec* specs, int count, cudaStream_t stream) {
     a.n_valid[i] = specs[i].n;
     a.k_valid[i] = specs[i].k;
   }
-  tc::tc_prep_b_batch_kernel<<<dim3((tc::TILE * tc::TILE + 255) / 256, count), 256, 0, stream>>>(a);
+  CGCN_CUDA(launch_k(tc::tc_prep_b_batch_kernel, dim3((tc::TILE * tc::TILE + 255) / 256, count), dim3(256), 0, stream, a));
   return check_launch("tc_prep_b_batch_kernel");
 }
 
@@ -641,7 +650,7 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
   const uint32_t* img = static_cast<const uint32_t*>(ready_image);      // prepared by tc_prep_images for this (B, n, k)
   if (img == nullptr) {
     uint32_t* fresh = static_cast<uint32_t*>(workspace);
-    tc::tc_prep_b_kernel<<<(tc::TILE * tc::TILE + 255) / 256, 256, 0, stream>>>(B, b_transposed, n, k, fresh);
+    CGCN_CUDA(launch_k(tc::tc_prep_b_kernel, dim3((tc::TILE * tc::TILE + 255) / 256), dim3(256), 0, stream, B, b_transposed, n, k, fresh));
     CGCN_TRY(check_launch("tc_prep_b_kernel"));
     img = fresh;
   }
@@ -673,7 +682,7 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
     }
     return check_launch("gemm_rowpanel_tc_kernel");
   }
-  tc::gemm_rowpanel_tc_kernel<<<grid, tc::THREADS, tc::RP_SMEM, stream>>>(p);
+  CGCN_CUDA(launch_k(tc::gemm_rowpanel_tc_kernel, dim3(grid), dim3(tc::THREADS), tc::RP_SMEM, stream, p));
   return check_launch("gemm_rowpanel_tc_kernel");
 }
 
@@ -697,7 +706,7 @@ int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float
   rows = (rows + tc::KCH - 1) / tc::KCH * tc::KCH;
   const int parts = static_cast<int>((m + rows - 1) / rows);
   tc::GramTcArgs p{A, lda, B, ldb, m, rows, static_cast<float*>(workspace), ka, nb};
-  tc::gemm_gram_tc_kernel<<<parts, tc::THREADS, tc::GR_SMEM, stream>>>(p);
+  CGCN_CUDA(launch_k(tc::gemm_gram_tc_kernel, dim3(parts), dim3(tc::THREADS), tc::GR_SMEM, stream, p));
   CGCN_TRY(check_launch("gemm_gram_tc_kernel"));
   gram_finalize_launch(p.partial, parts, tc::TILE * tc::TILE, tc::TILE, ka, nb, C, ldc, accumulate, stream);
   return check_launch("gram_finalize_kernel");

@@ -58,6 +58,32 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- programmatic dependent launch switches (common.cuh)
+bool pdl_enabled() {
+  static const bool on = getenv("CGCN_NO_PDL") == nullptr;
+  return on;
+}
+static thread_local cudaStream_t tls_plain[4] = {nullptr, nullptr, nullptr, nullptr};
+static thread_local bool tls_plain_set[4] = {false, false, false, false};
+void pdl_plain_next(cudaStream_t stream) {
+  for (int i = 0; i < 4; ++i)
+    if (tls_plain_set[i] && tls_plain[i] == stream) return;
+  for (int i = 0; i < 4; ++i)
+    if (!tls_plain_set[i]) {
+      tls_plain_set[i] = true;
+      tls_plain[i] = stream;
+      return;
+    }
+}
+bool pdl_take_plain(cudaStream_t stream) {
+  for (int i = 0; i < 4; ++i)
+    if (tls_plain_set[i] && tls_plain[i] == stream) {
+      tls_plain_set[i] = false;
+      return true;
+    }
+  return false;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -283,6 +309,7 @@ static const void* fwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.w
 static const void* bwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.ws + c.lay.img_bwd[i] : nullptr; }
 
 static int prep_fwd_images(const Ctx& c) {
+  pdl_plain_next(c.st);              // first kernel of a pass: ordinary stream order against whatever ran before
   if (!use_images(c.m)) return CGCN_OK;
   TcImageSpec sp[ML + 1];
   int k = 0;
@@ -394,6 +421,7 @@ struct Fork {
     if (serial) return CGCN_OK;
     CGCN_CUDA(cudaEventRecord(side->fork[id], st));
     CGCN_CUDA(cudaStreamWaitEvent(ss, side->fork[id], 0));
+    pdl_plain_next(ss);              // the next side-stream kernel depends on an event, not on its stream predecessor
     id = (id + 1) & 3;
     return CGCN_OK;
   }
@@ -401,6 +429,7 @@ struct Fork {
     if (serial) return CGCN_OK;
     CGCN_CUDA(cudaEventRecord(side->join, ss));
     CGCN_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    pdl_plain_next(st);
     return CGCN_OK;
   }
 };

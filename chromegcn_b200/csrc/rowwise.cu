@@ -147,13 +147,15 @@ static int launch_finalize(void (*kernel)(KArgs...), int gx, int cy, cudaStream_
   cfg.blockDim = dim3(32, FIN_SLICES, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = cy;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (pdl_enabled() && !pdl_take_plain(stream)) ? 2 : 1;
   CGCN_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
   return CGCN_OK;
 }
@@ -162,6 +164,7 @@ static int launch_finalize(void (*kernel)(KArgs...), int gx, int cy, cudaStream_
 
 template <int DV, int S, bool STATS>
 __global__ void __launch_bounds__(RW_THREADS) gate_fwd_kernel(const GateFwdArgs a) {
+  pdl_grid_sync();
   constexpr int D = DV * 128;
   constexpr int K = 2 * S * D;
   extern __shared__ __align__(16) float red[];
@@ -233,6 +236,7 @@ bn_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, int 
                    float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ num_batches,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out, const double* __restrict__ presummed,
                    double* __restrict__ sums_out) {
+  pdl_grid_sync();
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool active = c < D;
   const int K = 2 * S * D;
@@ -287,6 +291,7 @@ bn_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, int 
 // hb = dropout(gamma * (relu(h) - mean) * rstd + beta)      (models/ChromeModels.py:48-50)
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
+  pdl_grid_sync();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < a.total4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t e = i * 4;
@@ -309,6 +314,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 
 template <int DV, int S>
 __global__ void __launch_bounds__(RW_THREADS, (DV == 1) ? 4 : 1) bn_bwd_reduce_kernel(const BnBwdReduceArgs a) {
+  pdl_grid_sync();
   constexpr int D = DV * 128;
   constexpr int K = 2 * S * D;
   extern __shared__ __align__(16) float red[];
@@ -355,6 +361,7 @@ __global__ void __launch_bounds__(32 * FIN_SLICES)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, int D, int training, float* __restrict__ c1,
                        float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta,
                        const double* __restrict__ presummed, double* __restrict__ sums_out) {
+  pdl_grid_sync();
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool active = c < D;
   const int K = 2 * S * D;
@@ -403,6 +410,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int parts, int64_t n, 
 
 template <int DV, int S, int HEAD>
 __global__ void __launch_bounds__(RW_THREADS, (DV == 1) ? 3 : 1) gate_bwd_kernel(const GateBwdArgs a) {
+  pdl_grid_sync();
   constexpr int D = DV * 128;
   constexpr int K = 2 * D + 4;
   extern __shared__ __align__(16) float red[];
@@ -481,6 +489,7 @@ struct ColFinalizeArgs {
 };
 
 __global__ void __launch_bounds__(32 * FIN_SLICES) col_finalize_kernel(const ColFinalizeArgs a) {
+  pdl_grid_sync();
   const int t = blockIdx.x * 32 + threadIdx.x;        // index into the concatenation of the segments
   int q = -1, local = 0, base = 0;
 #pragma unroll
@@ -503,6 +512,7 @@ __global__ void __launch_bounds__(32 * FIN_SLICES) col_finalize_kernel(const Col
 // logit gradient).  One thread per column, 8 rows in flight.
 __global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols, int ld,
                                                              int64_t rows_per_cta, float* __restrict__ partial) {
+  pdl_grid_sync();
   const int c = threadIdx.x;
   const int64_t r0 = blockIdx.x * rows_per_cta;
   const int64_t r1 = min(r0 + rows_per_cta, rows);
@@ -534,6 +544,7 @@ struct BceArgs {
 
 template <int SS>
 __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
+  pdl_grid_sync();
   __shared__ float wsum[8];
   float local = 0.f;
   constexpr uint32_t S = SS;                                    // compile-time: the strand loads issue back to back
@@ -604,6 +615,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
 
 __global__ void __launch_bounds__(256) bce_finalize_kernel(const float* __restrict__ partial, int parts, float inv_count,
                                                             float* loss_sum) {
+  pdl_grid_sync();
   __shared__ double sh[256];
   double s = 0.0;
   for (int p = threadIdx.x; p < parts; p += 256) s += static_cast<double>(partial[p]);
@@ -619,6 +631,7 @@ __global__ void __launch_bounds__(256) bce_finalize_kernel(const float* __restri
 // ------------------------------------------------------------------------------ optimisers
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t count,
                            float lr, float momentum, float wd, float gscale) {
+  pdl_grid_sync();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= count) return;
   const float w = p[i];
@@ -632,6 +645,7 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t count, float lr, float b1, float b2, float eps,
                             float bc1, float bc2_sqrt, float gscale) {
+  pdl_grid_sync();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= count) return;
   const float gr = g[i] * gscale;
@@ -645,6 +659,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 // ------------------------------------------------------------------------------ utilities
 __global__ void interleave_kernel(const float* s0, const float* s1, int S, int64_t n, int d4, float4* dst) {
+  pdl_grid_sync();
   const int64_t total = n * S * d4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -657,6 +672,7 @@ __global__ void interleave_kernel(const float* s0, const float* s1, int S, int64
 }
 
 __global__ void deinterleave_kernel(const float* src, int S, int64_t n, int w, float* d0, float* d1) {
+  pdl_grid_sync();
   const int64_t total = n * S * w;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -668,6 +684,7 @@ __global__ void deinterleave_kernel(const float* src, int S, int64_t n, int w, f
 }
 
 __global__ void dropout_mask_kernel(float4* mask, int64_t total4, DropoutCfg cfg) {
+  pdl_grid_sync();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     mask[i] = cfg.enabled ? dropout_mult4(cfg, static_cast<uint64_t>(i)) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -707,9 +724,9 @@ int gate_fwd_launch(const GateFwdArgs& a, int d, int S, bool stats, int* grid_ou
 #define GF(DVC, SC)                                                                          \
   if (stats) {                                                                               \
     CGCN_TRY(ensure_smem(gate_fwd_kernel<DVC, SC, true>, smem));                             \
-    gate_fwd_kernel<DVC, SC, true><<<grid, RW_THREADS, smem, stream>>>(a);                   \
+    CGCN_CUDA(launch_k(gate_fwd_kernel<DVC, SC, true>, dim3(grid), dim3(RW_THREADS), smem, stream, a)); \
   } else {                                                                                   \
-    gate_fwd_kernel<DVC, SC, false><<<grid, RW_THREADS, 0, stream>>>(a);                     \
+    CGCN_CUDA(launch_k(gate_fwd_kernel<DVC, SC, false>, dim3(grid), dim3(RW_THREADS), 0, stream, a));   \
   }
   DISPATCH_DV_S(dv, S, GF);
 #undef GF
@@ -730,7 +747,7 @@ int bn_finalize_launch(const float* partial, int parts, int64_t n, int S, int D,
 }
 
 int bn_apply_launch(const BnApplyArgs& a, cudaStream_t stream) {
-  bn_apply_kernel<<<flat_grid(a.total4, 256), 256, 0, stream>>>(a);
+  CGCN_CUDA(launch_k(bn_apply_kernel, dim3(flat_grid(a.total4, 256)), dim3(256), 0, stream, a));
   return check_launch("bn_apply_kernel");
 }
 
@@ -741,7 +758,7 @@ int bn_bwd_reduce_launch(const BnBwdReduceArgs& a, int d, int S, int* grid_out, 
   const size_t smem = static_cast<size_t>(RW_WARPS) * 2 * S * d * sizeof(float);
 #define BR(DVC, SC)                                                    \
   CGCN_TRY(ensure_smem(bn_bwd_reduce_kernel<DVC, SC>, smem));          \
-  bn_bwd_reduce_kernel<DVC, SC><<<grid, RW_THREADS, smem, stream>>>(a);
+  CGCN_CUDA(launch_k(bn_bwd_reduce_kernel<DVC, SC>, dim3(grid), dim3(RW_THREADS), smem, stream, a));
   DISPATCH_DV_S(dv, S, BR);
 #undef BR
   return check_launch("bn_bwd_reduce_kernel");
@@ -770,10 +787,10 @@ int gate_bwd_launch(const GateBwdArgs& a, int d, int S, bool head, int* grid_out
 #define GBW(DVC, SC)                                                            \
   if (head) {                                                                   \
     CGCN_TRY(ensure_smem(gate_bwd_kernel<DVC, SC, 1>, smem));                   \
-    gate_bwd_kernel<DVC, SC, 1><<<grid, RW_THREADS, smem, stream>>>(a);         \
+    CGCN_CUDA(launch_k(gate_bwd_kernel<DVC, SC, 1>, dim3(grid), dim3(RW_THREADS), smem, stream, a)); \
   } else {                                                                      \
     CGCN_TRY(ensure_smem(gate_bwd_kernel<DVC, SC, 0>, smem));                   \
-    gate_bwd_kernel<DVC, SC, 0><<<grid, RW_THREADS, smem, stream>>>(a);         \
+    CGCN_CUDA(launch_k(gate_bwd_kernel<DVC, SC, 0>, dim3(grid), dim3(RW_THREADS), smem, stream, a)); \
   }
   DISPATCH_DV_S(dv, S, GBW);
 #undef GBW
@@ -805,7 +822,7 @@ int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* dst, fl
   int64_t rows_per = (rows + max_parts - 1) / max_parts;
   if (rows_per < 64) rows_per = 64;
   const int parts = static_cast<int>((rows + rows_per - 1) / rows_per);
-  colsum_partial_kernel<<<parts, 128, 0, stream>>>(X, rows, cols, ld, rows_per, partial);
+  CGCN_CUDA(launch_k(colsum_partial_kernel, dim3(parts), dim3(128), 0, stream, X, rows, cols, ld, rows_per, partial));
   CGCN_TRY(check_launch("colsum_partial_kernel"));
   ColFinalizeArgs f{};
   f.partial = partial;
@@ -827,10 +844,10 @@ int bce_launch(const float* out, const float* target, const uint32_t* target_bit
   int grid = static_cast<int>((a.total + 1023) / 1024);
   if (grid > bce_grid()) grid = bce_grid();
   if (grid < 1) grid = 1;
-  if (S == 1) bce_kernel<1><<<grid, 256, 0, stream>>>(a);
-  else bce_kernel<2><<<grid, 256, 0, stream>>>(a);
+  if (S == 1) CGCN_CUDA(launch_k(bce_kernel<1>, dim3(grid), dim3(256), 0, stream, a));
+  else CGCN_CUDA(launch_k(bce_kernel<2>, dim3(grid), dim3(256), 0, stream, a));
   CGCN_TRY(check_launch("bce_kernel"));
-  bce_finalize_kernel<<<1, 256, 0, stream>>>(partial, grid, a.inv_count, loss_sum);
+  CGCN_CUDA(launch_k(bce_finalize_kernel, dim3(1), dim3(256), 0, stream, partial, grid, a.inv_count, loss_sum));
   return check_launch("bce_finalize_kernel");
 }
 

@@ -85,6 +85,7 @@ spmm_pattern_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
                     const float* __restrict__ x, float* __restrict__ out, int scale_mode,
                     const float* __restrict__ residual, const float* __restrict__ vals,
                     const float* __restrict__ row_inv) {
+  pdl_grid_sync();
   constexpr size_t PITCH = static_cast<size_t>(VEC) * 128;
   __shared__ float4 red[SPMM_WARPS][VEC][32];
   const int lane = threadIdx.x & 31;
@@ -237,6 +238,7 @@ template <int VEC>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, (VEC <= 2) ? 5 : 2)
 spmm_peer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n, const PeerTable t,
                  float* __restrict__ out, int scale_mode, const float* __restrict__ residual) {
+  pdl_grid_sync();
   constexpr size_t PITCH = static_cast<size_t>(VEC) * 128;
   __shared__ float4 red[SPMM_WARPS][VEC][32];
   const int lane = threadIdx.x & 31;
@@ -379,11 +381,11 @@ int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int 
 #define SPMM_CASE(V)                                                                                                  \
   case V:                                                                                                             \
     if (weighted)                                                                                                     \
-      spmm_pattern_kernel<V, true><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, x, out, scale_mode, residual, \
-                                                               g->vals, g->row_inv);                                 \
+      CGCN_CUDA(launch_k(spmm_pattern_kernel<V, true>, grid, block, 0, stream, g->rowptr, g->colidx, g->n, x, out,    \
+                         scale_mode, residual, g->vals, g->row_inv));                                                 \
     else                                                                                                              \
-      spmm_pattern_kernel<V, false><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, x, out, scale_mode,      \
-                                                                residual, nullptr, nullptr);                          \
+      CGCN_CUDA(launch_k(spmm_pattern_kernel<V, false>, grid, block, 0, stream, g->rowptr, g->colidx, g->n, x, out,   \
+                         scale_mode, residual, nullptr, nullptr));                                                    \
     break;
   switch (vec) {
     SPMM_CASE(1)
