@@ -341,8 +341,15 @@ def main():
                 tot_bytes += g.nnz * (4 + 4 * W) + 4 * (g.n + 1) + 4 * W * g.n
                 n_launch += 1
         achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+        # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01b_spmm_traffic.json")
+        if args.workload == "wg" and world == 1 and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01b_spmm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches)" % tj["launches"]
         roofline = {"bound": "hbm", "kernel": "spmm_pattern_kernel<2> (forward mean aggregation, width 256)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": peak_src, "avg_launch_us": tot_ms * 1e3 / n_launch,
                     "algorithmic_bytes_per_launch": tot_bytes / n_launch,
                     "note": "algorithmic bytes nnz*(4+4W)+4(N+1)+4WN; Hi-C locality keeps most gathers in L2, so "

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const T* __re
 }
 
 // single CTA: exclusive scan of the block sums in place (sequential over chunks of 256 with a carry)
-__global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(unsigned* __restrict__ block_sums, int64_t nb) {
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(unsigned* __restrict__ block_sums, int64_t nb) {
   __shared__ unsigned ws[8];
   unsigned carry = 0;
   for (int64_t c = 0; c < nb; c += SCAN_THREADS) {

@@ -303,6 +303,24 @@ int cgcn_train_step(const cgcn_model* m, const float* target, float* probs, floa
 int cgcn_train_step_bits(const cgcn_model* m, const uint32_t* target_bits, float* probs, float* loss_sum_out,
                          float* out_grad_scratch);
 
+/* ------------------------------------------------------- split metrics ---- */
+/*
+ * Per-label ranking metrics of one split, replacing the sklearn calls of utils/metrics.py that
+ * utils/evals.py:86-90 makes once per split per epoch (runner.py:41,45,51) on the [n][nclass] probability
+ * matrix: roc_auc_score (utils/metrics.py:238-253), precision_recall_curve + auc (:168-183), the recall at
+ * the lowest threshold whose 1 - precision <= fdr_cutoff (:148-165) and average_precision_score (:25-26).
+ * preds [n][pred_ld] fp32 (device); labels either as floats targets [n][target_ld] (non-zero = positive) or as
+ * bit rows target_bits [n][(nclass+31)/32] (exactly one of the two non-NULL).
+ * out (device, double) [5][nclass]: AUROC (NaN for a label with a single class: roc_auc_score raises and the
+ * reference skips it), AUPR, recall at the cutoff, average precision, number of positives.
+ * Equal scores form one threshold, exactly like sklearn's distinct-threshold curves; results agree with
+ * sklearn to fp64 rounding (tests: 1e-9).  Enqueues on `stream`; no allocation, no synchronisation.
+ */
+size_t cgcn_label_metrics_workspace_bytes(int64_t n, int32_t nclass);
+int cgcn_label_metrics(const float* preds, int64_t pred_ld, const float* targets, int64_t target_ld,
+                       const uint32_t* target_bits, int64_t n, int32_t nclass, double fdr_cutoff, double* out,
+                       void* workspace, size_t workspace_bytes, cgcn_stream_t stream);
+
 /* ------------------------------------------------------------- optimiser ---- */
 /* torch.optim.SGD(lr, momentum, weight_decay) as built by utils/util_methods.py:18-19, over one flat
  * buffer: g += wd*p ; buf = momentum*buf + g ; p -= lr*buf.  grad_scale multiplies g first (1/world

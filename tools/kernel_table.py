@@ -5,7 +5,7 @@ nclass 103 (logit row pitch 104).  ncu times are cold-cache and serialised: read
 import csv, collections, re, sys, json
 
 path = sys.argv[1]
-peak = 6442.6
+peak = 6541.1
 N, NNZ, S, D, C, LD = 1183638, 12683638, 2, 128, 103, 104
 P = N * S * D * 4                    # one feature panel
 O = N * S * LD * 4                   # one logit panel
