@@ -71,7 +71,9 @@ def auroc(all_targets, all_predictions):
     vals = []
     for i in range(all_targets.shape[1]):
         try:
-            vals.append(skm.roc_auc_score(all_targets[:, i], all_predictions[:, i]))
+            v = skm.roc_auc_score(all_targets[:, i], all_predictions[:, i])
+            if not np.isnan(v):       # single-class label: sklearn of the reference's era raises (skipped at :245-246),
+                vals.append(v)        # sklearn >= 1.7 warns and returns NaN -- skipped here as well
         except ValueError:
             pass
     vals = np.array(vals)
