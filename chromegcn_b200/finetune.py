@@ -37,6 +37,7 @@ def clear_caches() -> None:
     _TARGETS.clear()
     _STAGING.clear()
     _PACKED.clear()
+    DEVICE_OUTPUTS.clear()
 
 
 def engine_for(model) -> ChromosomeEngine:
@@ -79,18 +80,22 @@ _TARGETS: Dict = {}          # (id(dict), data_ptrs) -> concatenated CPU targets
 _STAGING: Dict = {}          # (device, slot) -> persistent device staging buffers of the H2D pipeline
 
 
-def _staging(device, slot: int, n: int, d: int, nclass: int, bits: bool):
-    """Device staging buffers of pipeline slot `slot`: x_f, x_r and the targets (float `[n, nclass]`, or int32 bit
-    rows `[n, ceil(nclass/32)]`)."""
-    tcols, tdtype = ((nclass + 31) // 32, torch.int32) if bits else (nclass, torch.float32)
-    key = (str(device), slot, bits)
+def _staging(device, slot: int, n: int, d: int, nclass: int):
+    """Device staging buffers of pipeline slot `slot`: x_f, x_r and (for soft labels only) float targets."""
+    key = (str(device), slot)
     cur = _STAGING.get(key)
-    if cur is None or cur[0].shape[0] < n or cur[0].shape[1] != d or cur[2].shape[1] != tcols:
+    if cur is None or cur[0].shape[0] < n or cur[0].shape[1] != d or cur[2].shape[1] != nclass:
         rows = max(n, cur[0].shape[0] if cur is not None and cur[0].shape[1] == d else 0)
         cur = (torch.empty(rows, d, dtype=torch.float32, device=device), torch.empty(rows, d, dtype=torch.float32, device=device),
-               torch.empty(rows, tcols, dtype=tdtype, device=device))
+               torch.empty(rows, nclass, dtype=torch.float32, device=device))
         _STAGING[key] = cur
     return cur[0][:n], cur[1][:n], cur[2][:n]
+
+
+# What the last pass over a split left on the device: {split: (probabilities [sum N, nclass], label bit rows
+# [sum N, ceil(nclass/32)] or None)}.  `runner.run_model` computes the split's AUROC / AUPR / FDR from these
+# (cgcn_label_metrics) instead of from the CPU copies; valid until the next pass over the same split.
+DEVICE_OUTPUTS: Dict = {}
 
 
 _PACKED: Dict = {}           # id(target tensor) -> (weakref, version, pinned int32 bit rows | None for soft labels)
@@ -146,6 +151,14 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
         h2d = torch.cuda.Stream(device)
         d2h = torch.cuda.Stream(device)
         all_preds_dev = torch.empty(total_rows, nclass, dtype=torch.float32, device=device)
+        packed = ([packed_target(chrom_feature_dict[c]["target"]) for c in chroms]
+                  if (pack_labels and not resident) else [None] * len(chroms))
+        all_bits = all(p is not None for p in packed) and len(chroms) > 0
+        # bit rows are 16 B per window: they go straight into one [sum N, words] device matrix (no staging slot)
+        all_tbits_dev = (torch.empty(total_rows, (nclass + 31) // 32, dtype=torch.int32, device=device) if all_bits else None)
+        offsets = [0]
+        for c in chroms:
+            offsets.append(offsets[-1] + sizes[c])
         all_preds = torch.empty(total_rows, nclass, dtype=torch.float32, pin_memory=True)
         losses_dev = torch.zeros(max(len(chroms), 1), dtype=torch.float32, device=device)
         staged = [None, None]
@@ -162,14 +175,15 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
                 staged[k % 2] = ("resident",) + _RESIDENT[rkey]
                 return
             n, d = feats["forward"].shape
-            tgt_host = None if (resident or not pack_labels) else packed_target(feats["target"])
-            x_f, x_r, tgt = _staging(device, k % 2, n, d, nclass, tgt_host is not None)
+            x_f, x_r, tgt = _staging(device, k % 2, n, d, nclass)
+            if all_bits:
+                tgt = all_tbits_dev[offsets[k]: offsets[k + 1]]
             with torch.cuda.stream(h2d):
                 if k >= 2:
                     h2d.wait_event(consumed[k % 2])          # the slot's previous tenant has been packed / consumed
                 x_f.copy_(feats["forward"], non_blocking=True)
                 x_r.copy_(feats["backward"], non_blocking=True)
-                tgt.copy_(feats["target"] if tgt_host is None else tgt_host, non_blocking=True)
+                tgt.copy_(packed[k] if all_bits else feats["target"], non_blocking=True)
                 ready[k % 2].record(h2d)
             staged[k % 2] = ("fresh", x_f, x_r, tgt)
 
@@ -206,5 +220,6 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
         done.record(d2h)
         losses = losses_dev.cpu()                                            # the one sync of the split
         done.synchronize()
+    DEVICE_OUTPUTS[split] = (all_preds_dev, all_tbits_dev)
     total_loss = float(losses.double().sum().item()) if chroms else 0
     return all_preds, _all_targets(chrom_feature_dict, chroms), total_loss

@@ -12,8 +12,20 @@ import time
 
 import torch
 
+from . import finetune as _ft
 from .finetune import finetune
-from .metrics import compute_metrics
+from .metrics import compute_metrics as _compute_metrics_host
+from .metrics import compute_metrics_device
+
+
+def compute_metrics(preds, targs, loss, opt=None, elapsed=0.0, data_dict=None, cell_type=None, split=None):
+    """utils/evals.py:86-120.  The split's probabilities and label bits are still on the GPU after `finetune()`
+    (`finetune.DEVICE_OUTPUTS`), so the per-label AUROC / AUPR / FDR come from `cgcn_label_metrics` there; the
+    sklearn route on the CPU copies remains for soft labels and for `opt.device_metrics = False`."""
+    dev = _ft.DEVICE_OUTPUTS.get(split) if getattr(opt, "device_metrics", True) else None
+    if dev is not None and dev[1] is not None and dev[0].shape[0] == preds.shape[0] and dev[0].shape[0] > 0:
+        return compute_metrics_device(dev[0], dev[1], loss, opt, elapsed, data_dict, cell_type)
+    return _compute_metrics_host(preds, targs, loss, opt, elapsed, data_dict, cell_type)
 
 
 def run_epoch(WindowModel, ChromeModel, split_data, crit, optimizer, epoch, data_dict, opt, split):
@@ -72,15 +84,15 @@ def run_model(WindowModel, ChromeModel, train_data, valid_data, test_data, crit,
         if not getattr(opt, "load_gcn", False) and not getattr(opt, "test_only", False):
             train_preds, train_targs, train_loss, elpsd = run_epoch(WindowModel, ChromeModel, train_data, crit, optimizer,
                                                                     epoch, data_dict, opt, "train")
-            train_metrics = compute_metrics(train_preds, train_targs, train_loss, opt, elpsd, data_dict, opt.cell_type)
+            train_metrics = compute_metrics(train_preds, train_targs, train_loss, opt, elpsd, data_dict, opt.cell_type, "train")
             valid_preds, valid_targs, valid_loss, elpsd = run_epoch(WindowModel, ChromeModel, valid_data, crit, optimizer,
                                                                     epoch, data_dict, opt, "valid")
-            valid_metrics = compute_metrics(valid_preds, valid_targs, valid_loss, opt, elpsd, data_dict, opt.cell_type)
+            valid_metrics = compute_metrics(valid_preds, valid_targs, valid_loss, opt, elpsd, data_dict, opt.cell_type, "valid")
             valid_metrics_sum = valid_metrics["meanAUPR"] + valid_metrics["meanAUPR"] + valid_metrics["meanFDR"]
             valid_metrics_sums += [valid_metrics_sum]
         test_preds, test_targs, test_loss, elpsd = run_epoch(WindowModel, ChromeModel, test_data, crit, optimizer, epoch,
                                                              data_dict, opt, "test")
-        test_metrics = compute_metrics(test_preds, test_targs, test_loss, opt, elpsd, data_dict, opt.cell_type)
+        test_metrics = compute_metrics(test_preds, test_targs, test_loss, opt, elpsd, data_dict, opt.cell_type, "test")
         if logger is not None:
             logger.evaluate(train_metrics, valid_metrics, test_metrics, epoch, getattr(opt, "total_num_parameters", 0))
         save_logger.save(epoch, opt, ChromeModel, valid_metrics_sum, valid_metrics_sums, valid_preds, valid_targs, test_preds,

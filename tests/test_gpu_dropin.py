@@ -88,3 +88,21 @@ def test_run_model_two_epochs(tmp_path):
     # the checkpoint loads into the CPU oracle (== the reference's class layout)
     from oracle.gcn import ChromeGCNOracle
     ChromeGCNOracle(128, 128, nclass, 0.2, True, 2).load_state_dict(ck["model"])
+    # the run above took its metrics from the GPU (cgcn_label_metrics on the device-resident probabilities);
+    # the same run with the reference's sklearn route on the CPU copies must log the same numbers
+    assert ft.DEVICE_OUTPUTS["test"][1] is not None
+    ft.clear_caches()
+    opt.device_metrics = False
+    opt.model_name = str(tmp_path / "model_host_metrics")
+    torch.manual_seed(1)
+    m2 = ChromeGCN(128, 128, nclass, 0.2, True, 2).to(dev)
+    hist2 = run_model(None, m2, {c: feats[c] for c in split_of["train"]}, {c: feats[c] for c in split_of["valid"]},
+                      {c: feats[c] for c in split_of["test"]}, None, get_optimizer(m2, opt), None, opt, None, None)
+    for a, b in zip(hist, hist2):
+        assert a["train_loss"] == b["train_loss"] and a["test_loss"] == b["test_loss"]
+        assert abs(a["test_meanAUC"] - b["test_meanAUC"]) <= 1e-9 and abs(a["test_meanAUPR"] - b["test_meanAUPR"]) <= 1e-9
+    dev_log = open(tmp_path / "model" / "test.log").read().strip().splitlines()[1:]
+    host_log = open(tmp_path / "model_host_metrics" / "test.log").read().strip().splitlines()[1:]
+    for la, lb in zip(dev_log, host_log):
+        va, vb = [float(x) for x in la.split(",")], [float(x) for x in lb.split(",")]
+        assert max(abs(x - y) for x, y in zip(va, vb)) <= 1e-9
