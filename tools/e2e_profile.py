@@ -7,7 +7,8 @@ from chromegcn_b200.chrome_models import ChromeGCN
 from chromegcn_b200.optim import FlatSGD
 from oracle import adjacency as oadj
 dev = torch.device("cuda", 0)
-chroms = synthetic.WHOLE_GENOME[:int(sys.argv[1])] if len(sys.argv) > 1 else synthetic.WHOLE_GENOME
+arg = sys.argv[1] if len(sys.argv) > 1 else ""
+chroms = (arg.split(",") if "chr" in arg else synthetic.WHOLE_GENOME[:int(arg)] if arg else synthetic.WHOLE_GENOME)
 tmp = tempfile.mkdtemp(); gd = {}; feats = {}
 for c in chroms:
     h = synthetic.make_hic(c)
