@@ -31,6 +31,8 @@ struct RowPanelArgs {
   const float* rowscale_inv;
   int rowscale_group;
   int a_vec, c_vec;              // 128-bit access legal on A rows / C rows
+  int64_t ldb;                   // floats between consecutive rows of B as stored ([k][n], or [n][k] when transposed)
+  int accumulate;                // C += ... (k-blocked contractions wider than 128)
 };
 
 __device__ __forceinline__ void fma_8x8(float (&acc)[8][8], const float4 a0, const float4 a1, const float4 b0,
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_rowpanel_kernel(const RowPan
       j = idx - kk * GB;
     }
     float v = 0.f;
-    if (kk < p.k && j < p.n) v = p.b_transposed ? __ldg(p.B + static_cast<size_t>(j) * p.k + kk)
-                                                : __ldg(p.B + static_cast<size_t>(kk) * p.n + j);
+    if (kk < p.k && j < p.n) v = p.b_transposed ? __ldg(p.B + static_cast<size_t>(j) * p.ldb + kk)
+                                                : __ldg(p.B + static_cast<size_t>(kk) * p.ldb + j);
     Bs[kk * GB + j] = v;
   }
 
@@ -160,7 +162,16 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_rowpanel_kernel(const RowPan
         float4 v = make_float4(fmaf(acc[i][h * 4 + 0], s, bias_r[h * 4 + 0]), fmaf(acc[i][h * 4 + 1], s, bias_r[h * 4 + 1]),
                                fmaf(acc[i][h * 4 + 2], s, bias_r[h * 4 + 2]), fmaf(acc[i][h * 4 + 3], s, bias_r[h * 4 + 3]));
         if (p.c_vec && col + 3 < p.n) {
+          if (p.accumulate) {
+            const float4 o = ld4(dst + col);
+            v = make_float4(v.x + o.x, v.y + o.y, v.z + o.z, v.w + o.w);
+          }
           st4(dst + col, v);
+        } else if (p.accumulate) {
+          if (col + 0 < p.n) dst[col + 0] += v.x;
+          if (col + 1 < p.n) dst[col + 1] += v.y;
+          if (col + 2 < p.n) dst[col + 2] += v.z;
+          if (col + 3 < p.n) dst[col + 3] += v.w;
         } else {
           if (col + 0 < p.n) dst[col + 0] = v.x;
           if (col + 1 < p.n) dst[col + 1] = v.y;
@@ -174,13 +185,14 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_rowpanel_kernel(const RowPan
 
 int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                        int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int64_t ldb, int accumulate) {
+  if (ldb <= 0) ldb = b_transposed ? k : n;
   CGCN_REQUIRE(A && B && C, "cgcn_gemm_rowpanel: null operand");
   CGCN_REQUIRE(n >= 1 && n <= GB && k >= 1 && k <= GB, "cgcn_gemm_rowpanel: n=%d k=%d must be in [1,128]", n, k);
   CGCN_REQUIRE(lda >= k && ldc >= n, "cgcn_gemm_rowpanel: leading dimension too small");
   CGCN_REQUIRE((rowscale_rowptr == nullptr && rowscale_inv == nullptr) || rowscale_group >= 1, "cgcn_gemm_rowpanel: rowscale_group");
   if (m <= 0) return CGCN_OK;
-  RowPanelArgs p{A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, 0, 0};
+  RowPanelArgs p{A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, 0, 0, ldb, accumulate};
   p.a_vec = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
   p.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
   const int k_pad = (k + GBK - 1) / GBK * GBK;

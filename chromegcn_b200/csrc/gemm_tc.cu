@@ -167,7 +167,7 @@ __device__ __forceinline__ float lds32(uint32_t saddr) {
 // one contiguous 128-byte row segment: 4 full lines per warp instruction.
 __device__ __forceinline__ void store_block_coalesced(uint32_t stg, const uint4 (&o)[8], int lane, float* __restrict__ dst_base,
                                                       int64_t ld, int64_t row_first, int64_t row_limit, int col0,
-                                                      int col_limit) {
+                                                      int col_limit, bool accumulate = false) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) sts128(stg + (lane * STG_PITCH + 4 * j) * 4, o[j]);
   __syncwarp();
@@ -179,7 +179,14 @@ __device__ __forceinline__ void store_block_coalesced(uint32_t stg, const uint4 
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int64_t grow = row_first + it * 4 + rsub;
-    if (grow < row_limit && col < col_limit) *reinterpret_cast<uint4*>(dst_base + grow * ld + col) = v[it];
+    if (grow < row_limit && col < col_limit) {
+      if (accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(dst_base + grow * ld + col);
+        v[it] = make_uint4(__float_as_uint(__uint_as_float(v[it].x) + o.x), __float_as_uint(__uint_as_float(v[it].y) + o.y),
+                           __float_as_uint(__uint_as_float(v[it].z) + o.z), __float_as_uint(__uint_as_float(v[it].w) + o.w));
+      }
+      *reinterpret_cast<uint4*>(dst_base + grow * ld + col) = v[it];
+    }
   }
   __syncwarp();
 }
@@ -187,14 +194,14 @@ __device__ __forceinline__ void store_block_coalesced(uint32_t stg, const uint4 
 // ------------------------------------------------------------------ B image (weights) preparation
 // img[(hi|lo)][kchunk 4][n 128][32 floats] in the K-major SWIZZLE_128B layout; Bw(n,k) is the weight
 // that multiplies A[:,k] into C[:,n].
-__global__ void tc_prep_b_kernel(const float* __restrict__ B, int b_transposed, int n_valid, int k_valid,
+__global__ void tc_prep_b_kernel(const float* __restrict__ B, int b_transposed, int n_valid, int k_valid, int64_t ldb,
                                  uint32_t* __restrict__ img) {
   pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= TILE * TILE) return;
   const int n = idx >> 7, k = idx & 127;
   float v = 0.f;                                               // zero padding up to 128 x 128
-  if (n < n_valid && k < k_valid) v = b_transposed ? __ldg(B + n * k_valid + k) : __ldg(B + k * n_valid + n);
+  if (n < n_valid && k < k_valid) v = b_transposed ? __ldg(B + n * ldb + k) : __ldg(B + k * ldb + n);
   uint32_t hi, lo;
   split_tf32(v, hi, lo);
   const int kc = k >> 5, kk = k & 31;
@@ -245,6 +252,7 @@ struct RowPanelTcArgs {
   int rowscale_group;
   int n_valid, k_valid;        // <= 128; A rows hold round_up(k_valid, 4) readable floats, C rows round_up(n_valid, 4) writable
   long long* trace;            // developer aid (CGCN_TC_TRACE=1): per-role clock64() stamps of CTA 0, else NULL
+  int accumulate;              // C += ... (k-blocked contractions wider than 128)
 };
 
 #define TC_TRACE(slot, idx)                                                                   \
@@ -429,7 +437,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rowpanel_tc_kernel(const RowP
           o[j] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
         }
         if (warp == 0) TC_TRACE(6, static_cast<int>(it) * 8 + cc * 2);
-        store_block_coalesced(stg, o, lane, p.C, p.ldc, tile_row0 + warp * 32, r_end, cc * 32, n_store);
+        store_block_coalesced(stg, o, lane, p.C, p.ldc, tile_row0 + warp * 32, r_end, cc * 32, n_store, p.accumulate != 0);
         if (warp == 0) TC_TRACE(6, static_cast<int>(it) * 8 + cc * 2 + 1);
       }
       tc_fence_before();
@@ -632,8 +640,10 @@ int tc_prep_images(const TcImageSpec* specs, int count, cudaStream_t stream) {
 
 int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                      int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
-                     void* workspace, size_t workspace_bytes, const void* ready_image, cudaStream_t stream) {
+                     void* workspace, size_t workspace_bytes, const void* ready_image, cudaStream_t stream, int64_t ldb,
+                     int accumulate) {
   CGCN_REQUIRE(A && B && C, "cgcn_gemm_rowpanel: null operand");
+  if (ldb <= 0) ldb = b_transposed ? k : n;
   CGCN_REQUIRE(tc_rowpanel_supported(lda, ldc, n, k, A, C),
                "cgcn_gemm_rowpanel(tcgen05): needs n, k <= 128 and 16-byte aligned rows padded to a multiple of 4 floats");
   CGCN_REQUIRE(bias == nullptr || aligned16(bias), "cgcn_gemm_rowpanel(tcgen05): bias must be 16-byte aligned");
@@ -650,7 +660,7 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
   const uint32_t* img = static_cast<const uint32_t*>(ready_image);      // prepared by tc_prep_images for this (B, n, k)
   if (img == nullptr) {
     uint32_t* fresh = static_cast<uint32_t*>(workspace);
-    CGCN_CUDA(launch_k(tc::tc_prep_b_kernel, dim3((tc::TILE * tc::TILE + 255) / 256), dim3(256), 0, stream, B, b_transposed, n, k, fresh));
+    CGCN_CUDA(launch_k(tc::tc_prep_b_kernel, dim3((tc::TILE * tc::TILE + 255) / 256), dim3(256), 0, stream, B, b_transposed, n, k, ldb, fresh));
     CGCN_TRY(check_launch("tc_prep_b_kernel"));
     img = fresh;
   }
@@ -658,7 +668,7 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
   int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   const int64_t rows_per_cta = ((m + grid - 1) / grid + 7) / 8 * 8;
   grid = static_cast<int>((m + rows_per_cta - 1) / rows_per_cta);
-  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rows_per_cta, rowscale_rowptr, rowscale_inv, rowscale_group, n, k, nullptr};
+  tc::RowPanelTcArgs p{A, lda, img, bias, C, ldc, m, rows_per_cta, rowscale_rowptr, rowscale_inv, rowscale_group, n, k, nullptr, accumulate};
   static const bool trace = getenv("CGCN_TC_TRACE") != nullptr;
   if (trace) {                                                  // developer aid: synchronous, prints CTA 0's timeline
     long long* d = nullptr;

@@ -22,13 +22,14 @@ int spmm_peer_launch(const cgcn_graph* g, const cgcn_peer_panel* pp, float* out,
                      const float* residual, cudaStream_t stream);
 int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                        int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
-                       cudaStream_t stream);
+                       cudaStream_t stream, int64_t ldb = 0, int accumulate = 0);
 int gemm_gram_ffma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
                    int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gram_workspace_bytes(int64_t m);
 int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
                      int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
-                     void* workspace, size_t workspace_bytes, const void* ready_image, cudaStream_t stream);
+                     void* workspace, size_t workspace_bytes, const void* ready_image, cudaStream_t stream, int64_t ldb = 0,
+                     int accumulate = 0);
 int tc_prep_images(const TcImageSpec* specs, int count, cudaStream_t stream);
 int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int ka,
                  int nb, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -98,9 +99,11 @@ int sm_count() {
 
 // ---- dense dispatch
 static thread_local int tls_rp_ordinal = 0, tls_gr_ordinal = 0;   // developer aid (CGCN_TC_MASK_RP / _GR bitmasks)
-int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
-                           int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
-                           int impl, void* ws, size_t ws_bytes, cudaStream_t stream, const void* ready_image = nullptr) {
+// one <= 128 x 128 block of the weight operand; B (with leading dimension ldb) already points at the block
+static int gemm_rowpanel_block(const float* A, int64_t lda, const float* B, int b_transposed, int64_t ldb, const float* bias, float* C,
+                               int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv,
+                               int rowscale_group, int accumulate, int impl, void* ws, size_t ws_bytes, cudaStream_t stream,
+                               const void* ready_image) {
   static const char* dis = getenv("CGCN_TC_DISABLE");          // developer aid: "rowpanel", "gram" or "rowscale"
   bool tc_ok = tc_rowpanel_supported(lda, ldc, n, k, A, C) &&
                (ready_image != nullptr || (ws != nullptr && ws_bytes >= tc_workspace_bytes()));
@@ -109,17 +112,42 @@ int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_tr
   if (mask_s && !((atoi(mask_s) >> tls_rp_ordinal) & 1)) tc_ok = false;
   ++tls_rp_ordinal;
   if (impl == 2 && !tc_ok) {
-    set_error("cgcn_gemm_rowpanel: tcgen05 path needs n, k <= 128, 16-byte aligned rows of a multiple of 4 floats and a workspace");
+    set_error("cgcn_gemm_rowpanel: tcgen05 path needs 16-byte aligned rows of a multiple of 4 floats and a workspace");
     return CGCN_ERR_INVALID;
   }
   if (impl == 2 || (impl == 0 && tc_ok))
     return gemm_rowpanel_tc(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, ws, ws_bytes,
-                            ready_image, stream);
-  return gemm_rowpanel_ffma(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, stream);
+                            ready_image, stream, ldb, accumulate);
+  return gemm_rowpanel_ffma(A, lda, B, b_transposed, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv, rowscale_group, stream, ldb,
+                            accumulate);
 }
 
-int gemm_gram_dispatch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
-                       int ka, int nb, int accumulate, int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
+// C[m x n] = rowscale * (A[m x k] op(B)) + bias for any n, k: the weight operand is cut into <= 128 x 128 blocks
+// (d_model 256 / 512: BASELINE.json's stress configuration); the k-blocks of one column block accumulate into C
+// (bias with the first one; the row scale distributes over the sum).
+int gemm_rowpanel_dispatch(const float* A, int64_t lda, const float* B, int b_transposed, const float* bias, float* C,
+                           int64_t ldc, int64_t m, int n, int k, const int32_t* rowscale_rowptr, const float* rowscale_inv, int rowscale_group,
+                           int impl, void* ws, size_t ws_bytes, cudaStream_t stream, const void* ready_image = nullptr) {
+  CGCN_REQUIRE(n >= 1 && k >= 1, "cgcn_gemm_rowpanel: n=%d k=%d", n, k);
+  if (n <= 128 && k <= 128)
+    return gemm_rowpanel_block(A, lda, B, b_transposed, b_transposed ? k : n, bias, C, ldc, m, n, k, rowscale_rowptr, rowscale_inv,
+                               rowscale_group, 0, impl, ws, ws_bytes, stream, ready_image);
+  const int64_t ldb = b_transposed ? k : n;
+  for (int n0 = 0; n0 < n; n0 += 128) {
+    const int nn = (n - n0) < 128 ? (n - n0) : 128;
+    for (int k0 = 0; k0 < k; k0 += 128) {
+      const int kk = (k - k0) < 128 ? (k - k0) : 128;
+      const float* Bblk = b_transposed ? B + static_cast<int64_t>(n0) * ldb + k0 : B + static_cast<int64_t>(k0) * ldb + n0;
+      CGCN_TRY(gemm_rowpanel_block(A + k0, lda, Bblk, b_transposed, ldb, (k0 == 0 && bias != nullptr) ? bias + n0 : nullptr, C + n0,
+                                   ldc, m, nn, kk, rowscale_rowptr, rowscale_inv, rowscale_group, k0 > 0 ? 1 : 0, impl, ws, ws_bytes,
+                                   stream, nullptr));
+    }
+  }
+  return CGCN_OK;
+}
+
+static int gemm_gram_block(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
+                           int ka, int nb, int accumulate, int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
   static const char* dis = getenv("CGCN_TC_DISABLE");
   bool tc_ok = tc_gram_supported(lda, ldb, ka, nb, A, B);
   if (dis && (strstr(dis, "gram") || (strstr(dis, "head") && (ka != 128 || nb != 128)))) tc_ok = false;
@@ -127,12 +155,25 @@ int gemm_gram_dispatch(const float* A, int64_t lda, const float* B, int64_t ldb,
   if (mask_s && !((atoi(mask_s) >> tls_gr_ordinal) & 1)) tc_ok = false;
   ++tls_gr_ordinal;
   if (impl == 2 && !tc_ok) {
-    set_error("cgcn_gemm_gram: tcgen05 path needs ka, nb <= 128 and 16-byte aligned rows of a multiple of 4 floats");
+    set_error("cgcn_gemm_gram: tcgen05 path needs 16-byte aligned rows of a multiple of 4 floats");
     return CGCN_ERR_INVALID;
   }
   if (impl == 2 || (impl == 0 && tc_ok))
     return gemm_gram_tc(A, lda, B, ldb, C, ldc, m, ka, nb, accumulate, ws, ws_bytes, stream);
   return gemm_gram_ffma(A, lda, B, ldb, C, ldc, m, ka, nb, accumulate, ws, ws_bytes, stream);
+}
+
+// C[ka x nb] (+)= A^T B for any ka, nb: one <= 128 x 128 output block per launch pair (the reduction runs over all m rows
+// inside a launch, so blocks never accumulate into each other).
+int gemm_gram_dispatch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
+                       int ka, int nb, int accumulate, int impl, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  CGCN_REQUIRE(ka >= 1 && nb >= 1, "cgcn_gemm_gram: ka=%d nb=%d", ka, nb);
+  for (int a0 = 0; a0 < ka; a0 += 128)
+    for (int b0 = 0; b0 < nb; b0 += 128)
+      CGCN_TRY(gemm_gram_block(A + a0, lda, B + b0, ldb, C + static_cast<int64_t>(a0) * ldc + b0, ldc, m,
+                               (ka - a0) < 128 ? (ka - a0) : 128, (nb - b0) < 128 ? (nb - b0) : 128, accumulate, impl, ws, ws_bytes,
+                               stream));
+  return CGCN_OK;
 }
 
 // ---- side stream: weight-gradient contractions and gradient finalizes are off the critical path of the
@@ -224,7 +265,7 @@ static int validate(const cgcn_model* m, bool backward) {
   CGCN_REQUIRE(m != nullptr, "cgcn_model: null");
   CGCN_REQUIRE(m->graph.n >= 1 && m->graph.rowptr && m->graph.colidx, "cgcn_model: bad graph");
   CGCN_REQUIRE((m->graph.vals == nullptr) == (m->graph.row_inv == nullptr), "cgcn_model: weighted graphs need vals and row_inv");
-  CGCN_REQUIRE(m->d == 128, "cgcn_model: d=%d (the model path supports d = 128, the width main.py:62 fixes)", m->d);
+  CGCN_REQUIRE(m->d == 128 || m->d == 256 || m->d == 512, "cgcn_model: d=%d (supported: 128 -- the width main.py:62 fixes -- 256, 512)", m->d);
   CGCN_REQUIRE(m->nclass >= 1 && m->nclass <= 128, "cgcn_model: nclass=%d must be in [1,128]", m->nclass);
   CGCN_REQUIRE(m->layers >= 1 && m->layers <= ML, "cgcn_model: layers=%d (1..%d)", m->layers, ML);
   CGCN_REQUIRE(m->gate_off == 0 || m->gate_off == 1, "cgcn_model: gate_off=%d", m->gate_off);
@@ -303,7 +344,7 @@ static int layer_drop_site(int l) { return l == 0 ? 0 : l + 1; }
 // Weight images of the tcgen05 contractions, one launch per pass (the weights change only at the optimiser step).
 static bool use_images(const cgcn_model* m) {
   static const bool off = getenv("CGCN_NO_IMAGES") != nullptr;      // developer aid: per-contraction preparation
-  return m->gemm_impl != 1 && !off;
+  return m->gemm_impl != 1 && !off && m->d == 128;      // wider models prepare each 128 x 128 weight block in place
 }
 static const void* fwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.ws + c.lay.img_fwd[i] : nullptr; }
 static const void* bwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.ws + c.lay.img_bwd[i] : nullptr; }

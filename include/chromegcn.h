@@ -177,7 +177,9 @@ int cgcn_spmm_peer(const cgcn_graph* g, const cgcn_peer_panel* panel, float* out
  * bias [n] or NULL.  rowscale_rowptr: NULL, or the graph's rowptr: row r is scaled by
  * 1/deg(r / rowscale_group) (the D^-1 of A_hat^T applied to the input of the backward SpMM);
  * rowscale_inv: NULL, or the graph's row_inv (weighted graphs; takes precedence over rowscale_rowptr).
- * k, n <= 128.  The tcgen05 path needs lda, ldc multiples of 4 (rows padded to round_up(k|n, 4) floats).
+ * Any k, n: weight operands wider than 128 are cut into <= 128 x 128 blocks whose k-blocks accumulate into C
+ * (d_model 256 / 512); k, n <= 128 is the single-launch case.  The tcgen05 path needs lda, ldc multiples of 4 (rows
+ * padded to round_up(k|n, 4) floats).
  */
 int cgcn_gemm_rowpanel(const float* A, int64_t lda, const float* B, int32_t b_transposed, const float* bias,
                        float* C, int64_t ldc, int64_t m, int32_t n, int32_t k,
@@ -187,7 +189,7 @@ int cgcn_gemm_rowpanel(const float* A, int64_t lda, const float* B, int32_t b_tr
  * C[ka x nb] (+)= sum_r A[r][0:ka] (x) B[r][0:nb]   (weight gradients X^T G: a reduction over
  * all m rows; autograd of models/SubLayers.py:43 and models/ChromeModels.py:51).
  * Deterministic: per-CTA partial tiles in the workspace, reduced in a fixed order in fp64.
- * accumulate != 0 adds to C.  ka, nb <= 128.
+ * accumulate != 0 adds to C.  Any ka, nb (one launch pair per <= 128 x 128 block of C).
  */
 size_t cgcn_gemm_gram_workspace_bytes(int64_t m);
 int cgcn_gemm_gram(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
@@ -213,7 +215,7 @@ typedef struct cgcn_params {
 
 typedef struct cgcn_model {
   cgcn_graph graph;
-  int32_t d;              /* feature width, multiple of 128 */
+  int32_t d;              /* feature width: 128 (main.py:62), 256 or 512 */
   int32_t nclass;         /* <= 128 */
   int32_t layers;         /* 1 or 2 (the reference builds 2 iff gcn_layers == 2); 3..CGCN_MAX_LAYERS = extension */
   int32_t strands;        /* 1 = one forward() call; 2 = x_f and x_r of finetune.py:41-42 batched */

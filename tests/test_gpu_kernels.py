@@ -80,7 +80,11 @@ def test_spmm_isolated_rows_and_tiny_graph():
 @pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("m,k,n,bt,bias,scale", [(1000, 128, 128, False, True, False), (777, 128, 103, True, True, False),
                                                   (515, 103, 128, False, False, False), (4099, 128, 128, True, False, True),
-                                                  (130, 128, 128, False, False, False), (64, 37, 5, True, True, False)])
+                                                  (130, 128, 128, False, False, False), (64, 37, 5, True, True, False),
+                                                  # weight operands wider than one 128 x 128 block (d_model 256 / 512)
+                                                  (1000, 512, 512, False, True, False), (777, 512, 103, True, True, False),
+                                                  (515, 103, 512, False, False, False), (600, 256, 256, True, False, True),
+                                                  (300, 200, 300, False, True, False)])
 def test_gemm_rowpanel(impl, m, k, n, bt, bias, scale):
     from chromegcn_b200 import ops
     gen = torch.Generator().manual_seed(m)
@@ -104,7 +108,8 @@ def test_gemm_rowpanel(impl, m, k, n, bt, bias, scale):
 
 
 @pytest.mark.parametrize("impl", [1, 0])
-@pytest.mark.parametrize("m,ka,nb", [(5000, 128, 128), (70001, 103, 128), (33, 128, 128), (2049, 128, 128)])
+@pytest.mark.parametrize("m,ka,nb", [(5000, 128, 128), (70001, 103, 128), (33, 128, 128), (2049, 128, 128),
+                                     (5000, 512, 512), (3000, 103, 512), (2000, 256, 128), (700, 300, 200)])
 def test_gemm_gram(impl, m, ka, nb):
     from chromegcn_b200 import ops
     gen = torch.Generator().manual_seed(m)

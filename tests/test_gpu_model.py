@@ -139,6 +139,54 @@ def test_fused_engine_matches_reference(tag):
         assert torch.equal(p.grad, q.grad), k
 
 
+@pytest.mark.parametrize("d,gemm_impl", [(256, 0), (512, 0), (512, 1)])
+def test_wide_model_matches_fp64_oracle(d, gemm_impl):
+    """d_model 256 / 512 (BASELINE.json's stress configuration; the reference class is generic in nfeat,
+    models/ChromeModels.py:24-31): the fused step -- width-2d SpMM, weight operands cut into 128 x 128 blocks on
+    the tensor cores, DV = d/128 row kernels -- against the fp64 oracle on the same inputs."""
+    from chromegcn_b200 import synthetic
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.engine import ChromosomeEngine
+    from chromegcn_b200.graph import HiCGraph
+    from oracle import adjacency as oadj
+    h = synthetic.make_hic("chr22", hic_edges=8000, n_windows=900, n_bins=2400)
+    ip, ix = oadj.build_adjacency_numpy(h.window_starts, h.bin1, h.bin2, h.val, h.norm, 1, 8000)
+    n, nclass = ip.shape[0] - 1, 19
+    gen = torch.Generator().manual_seed(d)
+    xf, xr = torch.randn(n, d, generator=gen), torch.randn(n, d, generator=gen)
+    tgt = (torch.rand(n, nclass, generator=gen) < 0.2).float()
+    torch.manual_seed(3)
+    om = ogcn.stress_init_(ogcn.ChromeGCNOracle(d, d, nclass, 0.0, True, 2))
+    m = ChromeGCN(d, d, nclass, 0.0, True, 2)
+    m.load_state_dict(om.state_dict())
+    m = m.to(_dev()).train()
+    m.gemm_impl = gemm_impl
+    g = HiCGraph.from_csr_pattern(ip, ix, _dev())
+    eng = ChromosomeEngine(m, 2)
+    probs, loss = torch.empty(n, nclass, device=_dev()), torch.zeros(1, device=_dev())
+    xg = torch.empty(n, 2, d, device=_dev())
+    out, gates = eng.run(g, eng.pack(xf.to(_dev()), xr.to(_dev())), tgt.to(_dev()), probs, loss, train=True, input_grad=xg)
+    grads = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}
+    om = om.double().train()
+    lo, prob_o, pred_o, ex = ogcn.chromosome_step(om, xf.double(), xr.double(), tgt.double(),
+                                                  ogcn.coo_adjacency(ip, ix, torch.float64), None, True, input_grads=True)
+    xf64, xr64 = ex["x_f"], ex["x_r"]
+    assert ogcn.max_rel(out.mean(1).cpu(), pred_o) <= FWD_TOL
+    assert ogcn.max_rel(probs.cpu(), prob_o) <= FWD_TOL
+    assert abs(loss.item() - lo) <= FWD_TOL * abs(lo)
+    for k, q in om.named_parameters():
+        err = ogcn.max_rel(grads[k], q.grad)
+        assert err <= 5e-5, (k, err)
+    assert ogcn.max_rel(xg[:, 0].cpu(), xf64.grad) <= 5e-5 and ogcn.max_rel(xg[:, 1].cpu(), xr64.grad) <= 5e-5
+    # eval mode through the module API (one strand per call, models/ChromeModels.py:34-52)
+    m.eval()
+    om.eval()
+    with torch.no_grad():
+        _, o1, (g1, g2), _ = m(xf.to(_dev()), g, None)
+        _, o2, (h1, h2), _ = om(xf.double(), ogcn.coo_adjacency(ip, ix, torch.float64), None)
+    assert ogcn.max_rel(o1.cpu(), o2) <= FWD_TOL and ogcn.max_rel(g2.cpu(), h2) <= FWD_TOL
+
+
 def test_reference_sparse_tensor_is_accepted():
     """The adjacency the reference's own process_graph returns (torch sparse COO) drops in."""
     z = np.load(os.path.join(GOLDEN, "model_l2_stress.npz"))

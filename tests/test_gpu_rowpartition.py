@@ -141,3 +141,41 @@ def test_row_partition_two_gpus_matches_single_gpu(exchange):
     for r in (0, 1):
         for k, v in ret[r].items():
             assert v <= (1e-5 if not k.startswith("grad.") else 2e-5), (r, k, v)
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_phase_api_world1_d512_is_bit_identical(exchange):
+    """d_model 512 (BASELINE.json's stress configuration, width-1024 panels): the stage-by-stage path with identity
+    collectives reproduces the fused single-GPU step bit for bit."""
+    from chromegcn_b200 import dist as cdist, synthetic
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.engine import ChromosomeEngine
+    from chromegcn_b200.graph import HiCGraph
+    dev = torch.device("cuda", 0)
+    os.environ["CGCN_NO_SIDE_STREAM"] = "1"
+    d, nclass = 512, 11
+    h = synthetic.make_hic("chr21", hic_edges=5000, n_windows=700, n_bins=1900)
+    ip, ix = oadj.build_adjacency_numpy(h.window_starts, h.bin1, h.bin2, h.val, h.norm, 1, 5000)
+    rp, ci = oadj.pattern_with_selfloops(ip, ix)
+    n = rp.shape[0] - 1
+    gen = torch.Generator().manual_seed(9)
+    panel = torch.randn(n, 2, d, generator=gen).to(dev)
+    tgt = (torch.rand(n, nclass, generator=gen) < 0.3).float().to(dev)
+    runs = []
+    for mode in ("fused", exchange):
+        torch.manual_seed(4)
+        m = ogcn.stress_init_(ChromeGCN(d, d, nclass, 0.0, True, 2)).to(dev).train()
+        g = HiCGraph.from_csr_pattern(rp, ci, dev, add_selfloops=False)
+        loss = torch.zeros(1, device=dev)
+        if mode == "fused":
+            out, _ = ChromosomeEngine(m, 2).run(g, panel, tgt, None, loss, train=True)
+        else:
+            step = cdist.RowPartitionedStep(m, g, cdist.row_partition(n, 1), 0, 2, None, exchange=mode)
+            out, _ = step.run(panel, tgt, loss, train=True)
+            out = out.clone()
+            torch.cuda.synchronize(dev)
+            step.close()
+        runs.append((out.clone(), loss.clone(), {k: p.grad.clone() for k, p in m.named_parameters()}))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    for k in runs[0][2]:
+        assert torch.equal(runs[0][2][k], runs[1][2][k]), k
