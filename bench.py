@@ -197,6 +197,8 @@ def main():
     _lib.require_cuda()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from chromegcn_b200 import hostbind
+    binding = hostbind.bind_to_gpu(local_rank)      # before any pinned allocation (first touch decides the NUMA node)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()            # started here so that nvidia-smi is already looping when the timed region begins
@@ -220,7 +222,7 @@ def main():
         f = synthetic.make_features(c, n, D, NCLASS)
         feats_host[c] = {k: v.pin_memory() for k, v in f.items()}
         panels[c] = ops.interleave_strands([f["forward"].to(dev), f["backward"].to(dev)])
-        targets[c] = f["target"].to(dev)
+        targets[c] = ops.pack_targets(f["target"]).to(dev)      # label bit rows, the form finetune() feeds the loss kernel
         probs[c] = torch.empty(n, NCLASS, device=dev)
         local_edges += graphs[c].nnz
     edges_t = torch.tensor([local_edges], dtype=torch.float64, device=dev)
@@ -375,7 +377,7 @@ def main():
                            "l2": "inputs larger than L2 (126 MB): %.2f GB of resident feature panels + targets cycled per "
                                  "step, ~50 panel-sized passes per chromosome" % (
                                      sum(sizes[c] for c in chroms) * (2 * D * 4 + NCLASS * 4) / 1e9),
-                           "gemm_impl": args.gemm_impl, "final_loss_sum": final_loss},
+                           "gemm_impl": args.gemm_impl, "final_loss_sum": final_loss, "host_binding_rank0": binding},
                 "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
