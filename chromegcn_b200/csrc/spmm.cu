@@ -166,6 +166,7 @@ spmm_pattern_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
   }
 }
 
+
 // ------------------------------------------------------------------------------------------------
 // Peer-memory variant: the gathered panel is spread over the exchange buffers of the ranks that share one
 // row-partitioned graph (cgcn_peer_panel).  Same warp-per-row schedule; each lane resolves the owner of ITS

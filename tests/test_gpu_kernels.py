@@ -66,6 +66,38 @@ def test_spmm_matches_oracle(width, mean):
     assert ogcn.max_rel(got2, want + res.double()) <= 2e-6
 
 
+@pytest.mark.parametrize("width", [128, 256])
+@pytest.mark.parametrize("n", [1013, 37, 4500])
+def test_spmm_near_diagonal_graph_matches_oracle_and_peer_kernel(width, n):
+    """Near-diagonal (Hi-C-like) graphs: short-range pairs, 5 % long-range pairs, one hub row, isolated rows, n not
+    a multiple of the CTA's row count.  Checked against the fp64 oracle and, bit for bit, against the peer-memory
+    kernel with one block (both kernels sum a row's neighbours in CSR order)."""
+    from chromegcn_b200 import ops
+    rng = np.random.default_rng(n + width)
+    m = n * 8
+    i = rng.integers(0, n, m)
+    j = np.clip(i + rng.integers(-20, 21, m), 0, n - 1)
+    far = rng.random(m) < 0.05
+    j[far] = rng.integers(0, n, int(far.sum()))
+    if n > 800:                                                           # row 5: hub (> LONG_ROW entries)
+        hj = rng.choice(n, 700, replace=False)
+        i, j = np.concatenate([i, np.full(700, 5)]), np.concatenate([j, hj])
+    keep = (i != j) & (i % 97 != 3)                                       # rows 3, 100, 197, ... keep only their self loop
+    ip, ix = oadj._pairs_to_csr(n, i[keep], j[keep])
+    g = _graph(ip, ix)
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randn(n, width, generator=gen)
+    res = torch.randn(n, width, generator=gen)
+    a = ogcn.coo_adjacency(ip, ix, torch.float64).coalesce()
+    want = torch.sparse.mm(a, x.double())
+    got = ops.spmm(g, x.to(_dev()), mean=True, residual=res.to(_dev()))
+    assert ogcn.max_rel(got.cpu(), want + res.double()) <= 2e-6
+    same_order = ops.spmm_peer(g, [x.to(_dev())], 0, mean=True, residual=res.to(_dev()))
+    assert torch.equal(got, same_order)
+    plain = ops.spmm(g, x.to(_dev()), mean=False)
+    assert torch.equal(plain, ops.spmm_peer(g, [x.to(_dev())], 0, mean=False))
+
+
 def test_spmm_isolated_rows_and_tiny_graph():
     from chromegcn_b200 import ops
     ip = np.array([0, 0, 1, 2, 2], dtype=np.int32)        # rows 0 and 3 isolated -> self loop only
