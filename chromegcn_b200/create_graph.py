@@ -6,8 +6,10 @@ files (Juicer `RAWobserved` / `*norm` dumps, the windows bed file) and the same 
 pickles `{split}_graphs_{hic_edges}_{norm}norm.pkl` of `{chrom: scipy.sparse.csr_matrix float64}`
 (`data/7create_graph_new.py:147-149,197-202`), byte-identical `indptr` / `indices`.
 
-What changes is where the work happens: the text files are parsed once into arrays (pandas C
-parser, `float_precision='round_trip'` so every value equals Python's `float(str)`), and filter,
+What changes is where the work happens: the text files are parsed once into arrays by the library's
+multi-threaded memory-mapped parser (`cgcn_contacts_parse` / `cgcn_vector_parse`, csrc/ingest.cu; every value
+equals Python's `int(str)` / `float(str)`; `CGCN_TEXT_PARSER=pandas` selects the pandas C parser with
+`float_precision='round_trip'` instead), and filter,
 fp64 normalisation, dict-semantics dedup, stable top-K, symmetrisation and CSR assembly run on the
 GPU (`cgcn_adj_build`) instead of a per-row Python loop over a dict, a Python sort and a dense
 N x N matrix (`:67-120`).
@@ -36,15 +38,47 @@ def read_window_starts(bed_file: str, chroms) -> Dict[str, np.ndarray]:
     return out
 
 
-def read_norm_vector(path: str) -> np.ndarray:
+def _native_parser() -> bool:
+    return os.environ.get("CGCN_TEXT_PARSER", "native") != "pandas"
+
+
+def _count_rows(lib, path: str, threads: int) -> int:
+    import ctypes as C
+    from . import _lib
+    rows = C.c_int64(0)
+    _lib.check(lib.cgcn_text_count_rows(os.fsencode(path), threads, C.byref(rows)), "cgcn_text_count_rows")
+    return int(rows.value)
+
+
+def read_norm_vector(path: str, threads: int = 0) -> np.ndarray:
     """`get_normalization_values` (:51-65) minus the NaN / 0 -> inf substitution, which the kernel applies."""
+    if _native_parser():
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        n = _count_rows(lib, path, threads)
+        out = np.empty(n, dtype=np.float64)
+        rows = C.c_int64(0)
+        _lib.check(lib.cgcn_vector_parse(os.fsencode(path), n, out.ctypes.data, C.byref(rows), threads), "cgcn_vector_parse")
+        return out[: int(rows.value)]
     import pandas as pd
     return pd.read_csv(path, sep="\t", header=None, usecols=[0], names=["v"], dtype={"v": np.float64},
                        float_precision="round_trip", na_values=["NaN", "nan"], keep_default_na=True)["v"].to_numpy()
 
 
-def read_contacts(path: str):
+def read_contacts(path: str, threads: int = 0):
     """The `start_pos1 \\t start_pos2 \\t val` triplets of a RAWobserved dump (:71-76)."""
+    if _native_parser():
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        n = _count_rows(lib, path, threads)
+        b1, b2, v = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64), np.empty(n, dtype=np.float64)
+        rows = C.c_int64(0)
+        _lib.check(lib.cgcn_contacts_parse(os.fsencode(path), n, b1.ctypes.data, b2.ctypes.data, v.ctypes.data, C.byref(rows),
+                                           threads), "cgcn_contacts_parse")
+        k = int(rows.value)
+        return b1[:k], b2[:k], v[:k]
     import pandas as pd
     df = pd.read_csv(path, sep="\t", header=None, usecols=[0, 1, 2], names=["b1", "b2", "v"],
                      dtype={"b1": np.int64, "b2": np.int64, "v": np.float64}, float_precision="round_trip")

@@ -65,6 +65,20 @@ int64_t cgcn_launch_count(void);
 
 /* ------------------------------------------------- piece 1: adjacency build ---- */
 /*
+ * Text ingest (host code, no CUDA call): the Juicer files data/7create_graph_new.py reads line by line with
+ * csv.DictReader.  cgcn_contacts_parse: `RAWobserved` dump, "bin1 \t bin2 \t value" per line (:71-76; further
+ * columns ignored, blank lines skipped) -> three arrays in file order.  cgcn_vector_parse: `*norm` vector, one
+ * float per line (:56-59; "NaN" parses to NaN -- the build kernel applies the NaN / 0 -> inf rule of :60-63).
+ * The file is memory-mapped and parsed by `threads` host threads (0 = all cores) over line-aligned byte ranges;
+ * numbers convert like Python's int() / float() on the same token (correctly rounded).  Size the arrays with
+ * cgcn_text_count_rows (non-blank lines).  A malformed line is CGCN_ERR_DATA with the row in cgcn_last_error().
+ */
+int cgcn_text_count_rows(const char* path, int32_t threads, int64_t* rows_out);
+int cgcn_contacts_parse(const char* path, int64_t capacity, int64_t* bin1, int64_t* bin2, double* val,
+                        int64_t* rows_out, int32_t threads);
+int cgcn_vector_parse(const char* path, int64_t capacity, double* out, int64_t* rows_out, int32_t threads);
+
+/*
  * Hi-C contact list -> symmetric binary window adjacency in CSR (no self loops).
  * Replaces data/7create_graph_new.py:67-120 (get_contact_edge_pairs, get_top_contact_locs,
  * create_adj_mat) bit-exactly:
