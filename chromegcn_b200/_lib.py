@@ -11,7 +11,7 @@ from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libchromegcn.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LAYERS = 4
 MAX_PEERS = 8
 

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CGCN_ABI_VERSION 5
+#define CGCN_ABI_VERSION 6
 #define CGCN_MAX_LAYERS 4
 #define CGCN_MAX_PEERS 8    /* GPUs of one NVSwitch box */
 
