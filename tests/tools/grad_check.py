@@ -1,6 +1,6 @@
 """Per-parameter gradient error of the fused step on a chr22-sized graph, FFMA vs tcgen05 contractions."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from chromegcn_b200 import synthetic
 from chromegcn_b200.chrome_models import ChromeGCN

@@ -11,7 +11,6 @@ from chromegcn_b200 import ops, synthetic, dist as cdist
 from chromegcn_b200.chrome_models import ChromeGCN
 from chromegcn_b200.graph import HiCGraph
 from chromegcn_b200.optim import FlatSGD
-from oracle import adjacency as oadj    # only for the +I pattern helper on the host (test/bench infrastructure)
 
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
 k_pairs = int(float(sys.argv[2])) if len(sys.argv) > 2 else 25_000_000

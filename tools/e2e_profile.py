@@ -5,7 +5,6 @@ from scipy import sparse
 from chromegcn_b200 import ops, synthetic, finetune as ft
 from chromegcn_b200.chrome_models import ChromeGCN
 from chromegcn_b200.optim import FlatSGD
-from oracle import adjacency as oadj
 dev = torch.device("cuda", 0)
 arg = sys.argv[1] if len(sys.argv) > 1 else ""
 chroms = (arg.split(",") if "chr" in arg else synthetic.WHOLE_GENOME[:int(arg)] if arg else synthetic.WHOLE_GENOME)
