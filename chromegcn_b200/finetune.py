@@ -118,6 +118,18 @@ def packed_target(target: torch.Tensor):
     return packed
 
 
+_STREAMS: Dict = {}          # device -> (h2d, d2h) copy streams, created once
+
+
+def _copy_streams(device):
+    key = str(device)
+    st = _STREAMS.get(key)
+    if st is None:
+        st = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        _STREAMS[key] = st
+    return st
+
+
 def _all_targets(chrom_feature_dict, chroms):
     key = (id(chrom_feature_dict), tuple(chrom_feature_dict[c]["target"].data_ptr() for c in chroms))
     t = _TARGETS.get(key)
@@ -148,8 +160,7 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
     total_rows = sum(sizes.values())
     main = torch.cuda.current_stream(device)
     with torch.cuda.device(device):
-        h2d = torch.cuda.Stream(device)
-        d2h = torch.cuda.Stream(device)
+        h2d, d2h = _copy_streams(device)
         all_preds_dev = torch.empty(total_rows, nclass, dtype=torch.float32, device=device)
         packed = ([packed_target(chrom_feature_dict[c]["target"]) for c in chroms]
                   if (pack_labels and not resident) else [None] * len(chroms))

@@ -504,3 +504,57 @@ def test_extension_variants_match_oracle(layers, gate):
         _, o2, og, _ = om(x_f.double(), adj)
     assert ogcn.max_rel(o1.cpu(), o2) <= FWD_TOL
     assert (g2 is None) == (layers == 1) and len(m.last_gates) == layers
+
+
+def test_sharded_epoch_round_is_one_step_on_the_mean_gradient():
+    """Chromosome-sharded data parallelism: a round = the chromosomes the ranks process at the
+    same weights, ONE optimiser step on the mean of their gradients.  On one rank a cell holding several chromosomes
+    goes through the same accumulate / scale / step code as the all-reduce path; the result must equal the oracle's
+    per-chromosome gradients (finetune.py:39-48 at fixed weights) averaged and applied by SGD
+    (utils/util_methods.py:18-19)."""
+    from chromegcn_b200 import dist as cdist, synthetic, ops
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.engine import ChromosomeEngine
+    from chromegcn_b200.graph import HiCGraph
+    from chromegcn_b200.optim import FlatSGD
+    from oracle import adjacency as oadj
+    nclass, chroms = 9, ["chr20", "chr21", "chr22"]
+    graphs, og, feats, panels, targets, probs = {}, {}, {}, {}, {}, {}
+    for i, c in enumerate(chroms):
+        h = synthetic.make_hic(c, hic_edges=3000, n_windows=300 + 40 * i, n_bins=900)
+        ip, ix = oadj.build_adjacency_numpy(h.window_starts, h.bin1, h.bin2, h.val, h.norm, 1, 3000)
+        n = ip.shape[0] - 1
+        og[c] = ogcn.coo_adjacency(ip, ix, torch.float64)
+        graphs[c] = HiCGraph.from_csr_pattern(ip, ix, _dev())
+        feats[c] = synthetic.make_features(c, n, 128, nclass)
+        panels[c] = ops.interleave_strands([feats[c]["forward"].to(_dev()), feats[c]["backward"].to(_dev())])
+        targets[c] = feats[c]["target"].to(_dev())
+        probs[c] = torch.empty(n, nclass, device=_dev())
+    torch.manual_seed(2)
+    om = ogcn.stress_init_(ogcn.ChromeGCNOracle(128, 128, nclass, 0.0, True, 2))
+    m = ChromeGCN(128, 128, nclass, 0.0, True, 2)
+    m.load_state_dict(om.state_dict())
+    m = m.to(_dev()).train()
+    m.gemm_impl = 1
+    om = om.double().train()
+    schedule = [[["chr20", "chr22"]], [["chr21"]]]                 # round 1: two chromosomes at the same weights
+    losses = torch.zeros(3, device=_dev())
+    opt = FlatSGD(m, lr=0.25)
+    cdist.sharded_train_epoch(ChromosomeEngine(m, 2), opt, schedule, 0, graphs, panels, targets, probs, losses)
+    oopt = ogcn.make_optimizer(om, "sgd", 0.25)
+    want_losses = []
+    for rnd in schedule:
+        acc = None
+        for c in rnd[0]:
+            oopt.zero_grad()
+            lo, _, _, _ = ogcn.chromosome_step(om, feats[c]["forward"].double(), feats[c]["backward"].double(),
+                                               feats[c]["target"].double(), og[c], None, True)
+            want_losses.append(lo)
+            g = [p.grad.clone() for p in om.parameters()]
+            acc = g if acc is None else [a + b for a, b in zip(acc, g)]
+        for p, a in zip(om.parameters(), acc):
+            p.grad = a / len(rnd[0])
+        oopt.step()
+    assert ogcn.max_rel(losses.cpu(), torch.tensor(want_losses)) <= FWD_TOL
+    for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
+        assert ogcn.max_rel(p.detach().cpu(), q.detach()) <= 2e-5, k
