@@ -111,6 +111,8 @@ def build_adjacency_numpy(window_starts, bin1, bin2, val, norm: Optional[np.ndar
         if k_pairs > 0:                                       # first K accepted rows (:88-89)
             i, j, v = i[:k_pairs], j[:k_pairs], v[:k_pairs]
 
+    if i.shape[0] == 0:                                       # nothing accepted: empty adjacency
+        return _pairs_to_csr(n, i, j)
     key = i * np.int64(n) + j
     order = np.argsort(key, kind="stable")                    # groups; file order inside a group
     ks = key[order]

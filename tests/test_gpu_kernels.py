@@ -302,6 +302,28 @@ def test_adjacency_edge_cases():
         ops.adjacency_build(w, np.array([0]), np.array([5000]), np.array([np.nan]), norm, 1, 10)
 
 
+def test_adjacency_build_random_small_cases_vs_loop_oracle():
+    """150 seeded adversarial cases (heavy value ties, duplicate and reversed keys, NaN / 0 norm entries, diagonal and
+    non-window rows, K from 0 to more than the candidates, with and without the norm vector) through cgcn_adj_build,
+    byte-compared with the record-at-a-time restatement of data/7create_graph_new.py:67-120."""
+    from chromegcn_b200 import ops
+    rng = np.random.default_rng(2024)
+    vals_pool = np.array([0.0, 1.0, 2.0, 2.0, 3.0, 5.5, 7.0])
+    norm_pool = np.array([1.0, 0.5, 2.0, np.nan, 0.0, 1.25])
+    for case in range(150):
+        n_bins = int(rng.integers(4, 60))
+        starts = np.sort(rng.choice(n_bins, int(rng.integers(1, n_bins + 1)), replace=False)).astype(np.int64) * 1000
+        m = int(rng.integers(0, 200))
+        b1 = rng.integers(0, n_bins, m).astype(np.int64) * 1000
+        b2 = rng.integers(0, n_bins, m).astype(np.int64) * 1000
+        v = vals_pool[rng.integers(0, len(vals_pool), m)]
+        norm = norm_pool[rng.integers(0, len(norm_pool), n_bins)] if case % 3 else None
+        hic_edges = int(rng.integers(0, 2 * m + 5))
+        want = oadj.build_adjacency_loops(starts, b1, b2, v, norm, 1, hic_edges)
+        got = ops.adjacency_build(starts, b1, b2, v, norm, 1, hic_edges, _dev())
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (case, n_bins, m, hic_edges)
+
+
 def test_process_graph_golden():
     from scipy import sparse
     from chromegcn_b200.graph import process_graph, HiCGraph
