@@ -61,7 +61,8 @@ def _worker(rank, world, port, ret):
         losses = torch.zeros(max(len(mine), 1), device=dev)
         cdist.sharded_train_epoch(ChromosomeEngine(m, 2), FlatSGD(m, lr=0.25), schedule, rank, graphs, panels, targets, probs, losses)
         torch.cuda.synchronize(dev)
-        ret[rank] = {"schedule": schedule, "params": {k: v.detach().cpu() for k, v in m.state_dict().items()}}
+        # numpy arrays pickle by value (tensors would travel as shared-memory handles through the manager process)
+        ret[rank] = {"schedule": schedule, "params": {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}}
     finally:
         dist.destroy_process_group()
 
@@ -84,7 +85,9 @@ def test_chromosome_sharded_pass_two_gpus_matches_mean_gradient_oracle():
     a, b = ret[0], ret[1]
     assert a["schedule"] == b["schedule"]
     for k in a["params"]:
-        assert torch.equal(a["params"][k], b["params"][k]), k               # replicas stay bit-identical
+        if "running" in k or "num_batches" in k:
+            continue                       # BatchNorm buffers: running statistics of the rank's own chromosomes
+        assert np.array_equal(a["params"][k], b["params"][k]), k            # replicas stay bit-identical
     # oracle: per round one SGD step on the mean gradient of the round's chromosomes (both ranks')
     data = _inputs()
     om = ogcn.ChromeGCNOracle(128, 128, NCLASS, 0.0, True, 2)
@@ -107,5 +110,5 @@ def test_chromosome_sharded_pass_two_gpus_matches_mean_gradient_oracle():
     want = om.state_dict()
     for k, v in a["params"].items():
         if "num_batches" in k or "running" in k:
-            continue                       # BatchNorm buffers are per-rank running statistics of the rank's own chromosomes
-        assert ogcn.max_rel(v, want[k]) <= 2e-5, k
+            continue
+        assert ogcn.max_rel(torch.from_numpy(v), want[k]) <= 2e-5, k
