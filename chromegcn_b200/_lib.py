@@ -89,6 +89,7 @@ PROTOTYPES = {
     "cgcn_text_count_rows": (C.c_int, [C.c_char_p, _I32, _P]),
     "cgcn_contacts_parse": (C.c_int, [C.c_char_p, _I64, _P, _P, _P, _P, _I32]),
     "cgcn_vector_parse": (C.c_int, [C.c_char_p, _I64, _P, _P, _I32]),
+    "cgcn_bed_starts_parse": (C.c_int, [C.c_char_p, C.c_char_p, _I64, _P, _P, _P, _I32]),
     "cgcn_label_metrics_workspace_bytes": (_SZ, [_I64, _I32]),
     "cgcn_label_metrics": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, C.c_double, _P, _P, _SZ, _P]),
     "cgcn_train_step": (C.c_int, [C.POINTER(Model), _P, _P, _P, _P]),

@@ -26,6 +26,22 @@ import numpy as np
 def read_window_starts(bed_file: str, chroms) -> Dict[str, np.ndarray]:
     """`create_bin_dict` (data/7create_graph_new.py:14-47): per chromosome the sorted unique start
     positions of the bed rows; a window's index is its rank."""
+    if _native_parser():
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        names = list(chroms)
+        joined = "\n".join(names).encode()
+        rows = C.c_int64(0)
+        rc = lib.cgcn_bed_starts_parse(os.fsencode(bed_file), joined, 0, None, None, C.byref(rows), 0)
+        if rc not in (0, -5):                                  # -5 = CGCN_ERR_CAPACITY: the sizing call
+            _lib.check(rc, "cgcn_bed_starts_parse")
+        n = int(rows.value)
+        ci, st = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+        if n:
+            _lib.check(lib.cgcn_bed_starts_parse(os.fsencode(bed_file), joined, n, ci.ctypes.data, st.ctypes.data, C.byref(rows), 0),
+                       "cgcn_bed_starts_parse")
+        return {c: np.unique(st[ci == i]) for i, c in enumerate(names)}
     import pandas as pd
     df = pd.read_csv(bed_file, sep="\t", header=None, usecols=[0, 1], names=["chrom", "start"],
                      dtype={"chrom": str, "start": np.int64})

@@ -49,6 +49,16 @@ inline int check_launch(const char* what) {
 
 int sm_count();                       // cached, current device
 
+// "set once per device" helper for cudaFuncSetAttribute: the attribute belongs to the device's context, so a
+// process that drives several GPUs must set it on each of them.
+inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 // ------------------------------------------------------------------ programmatic dependent launch
 // One chromosome step is ~34 kernels of 5..60 us each on one stream: the drain / launch / ramp-up bubble between
 // two dependent kernels is a measurable share of it.  Every kernel of the model path starts with pdl_grid_sync()

@@ -197,11 +197,10 @@ int gemm_rowpanel_ffma(const float* A, int64_t lda, const float* B, int b_transp
   p.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
   const int k_pad = (k + GBK - 1) / GBK * GBK;
   const size_t smem = static_cast<size_t>(k_pad * GB + 2 * GBK * GB) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     CGCN_CUDA(cudaFuncSetAttribute(gemm_rowpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (GB * GB + 2 * GBK * GB) * static_cast<int>(sizeof(float))));
-    attr_set = true;
   }
   const int64_t tiles = (m + GB - 1) / GB;
   const int grid = static_cast<int>(tiles < 2LL * sm_count() ? tiles : 2LL * sm_count());

@@ -652,10 +652,9 @@ int gemm_rowpanel_tc(const float* A, int64_t lda, const float* B, int b_transpos
     return CGCN_ERR_WORKSPACE;
   }
   if (m <= 0) return CGCN_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_rowpanel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::RP_SMEM));
-    attr_set = true;
   }
   const uint32_t* img = static_cast<const uint32_t*>(ready_image);      // prepared by tc_prep_images for this (B, n, k)
   if (img == nullptr) {
@@ -705,10 +704,9 @@ int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float
     set_error("cgcn_gemm_gram(tcgen05): workspace %zu < %zu bytes", workspace_bytes, gram_workspace_bytes(m));
     return CGCN_ERR_WORKSPACE;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GR_SMEM));
-    attr_set = true;
   }
   // one CTA per SM (the kernel owns the whole shared memory): a single wave, <= #SM partial tiles
   int64_t rows = (m + sm_count() - 1) / sm_count();

@@ -247,3 +247,77 @@ extern "C" int cgcn_vector_parse(const char* path, int64_t capacity, double* out
   *rows_out = off[T];
   return CGCN_OK;
 }
+
+// Windows bed file (create_bin_dict, data/7create_graph_new.py:24-37): "chrom \t start \t ..." per line.  For every
+// row whose chromosome is one of `chroms` (a '\n'-separated list of names) emits its index in that list and its start
+// position, in file order; the caller keeps the sorted unique starts per chromosome (:40-44).
+extern "C" int cgcn_bed_starts_parse(const char* path, const char* chroms, int64_t capacity, int32_t* chrom_index,
+                                     int64_t* start, int64_t* rows_out, int32_t threads) {
+  CGCN_REQUIRE(rows_out != nullptr && chroms != nullptr && capacity >= 0 && (capacity == 0 || (chrom_index && start)),
+               "cgcn_bed_starts_parse: null argument");
+  std::vector<std::string> names;
+  for (const char* b = chroms; *b;) {
+    const char* e = strchr(b, '\n');
+    if (!e) e = b + strlen(b);
+    if (e > b) names.emplace_back(b, e);
+    b = *e ? e + 1 : e;
+  }
+  Mapped m;
+  CGCN_TRY(map_file(path, &m));
+  *rows_out = 0;
+  if (m.size == 0) return CGCN_OK;
+  const int T = pick_threads(threads, m.size);
+  const std::vector<size_t> cut = line_cuts(m, T);
+  auto match = [&](const char* b, const char* e) -> int {
+    const size_t len = static_cast<size_t>(e - b);
+    for (size_t i = 0; i < names.size(); ++i)
+      if (names[i].size() == len && memcmp(names[i].data(), b, len) == 0) return static_cast<int>(i);
+    return -1;
+  };
+  // pass 1: matching rows per range
+  std::vector<int64_t> counts(T, 0);
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t)
+      pool.emplace_back([&, t] {
+        int64_t c = 0;
+        for_each_line(m.data + cut[t], m.data + cut[t + 1], [&](const char* b, const char* e) {
+          const char* t1 = static_cast<const char*>(memchr(b, '\t', static_cast<size_t>(e - b)));
+          if (t1 && match(b, t1) >= 0) ++c;
+        });
+        counts[t] = c;
+      });
+    for (auto& th : pool) th.join();
+  }
+  std::vector<int64_t> off(T + 1, 0);
+  for (int t = 0; t < T; ++t) off[t + 1] = off[t] + counts[t];
+  if (off[T] > capacity) {
+    *rows_out = off[T];                                        // the caller sizes its arrays from this and calls again
+    set_error("cgcn_bed_starts_parse: %lld matching rows, capacity %lld", static_cast<long long>(off[T]),
+              static_cast<long long>(capacity));
+    return CGCN_ERR_CAPACITY;
+  }
+  Failure fail;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < T; ++t)
+    pool.emplace_back([&, t] {
+      int64_t row = off[t];
+      for_each_line(m.data + cut[t], m.data + cut[t + 1], [&](const char* b, const char* e) {
+        const char* t1 = static_cast<const char*>(memchr(b, '\t', static_cast<size_t>(e - b)));
+        if (!t1) return;
+        const int ci = match(b, t1);
+        if (ci < 0) return;
+        const char* t2 = static_cast<const char*>(memchr(t1 + 1, '\t', static_cast<size_t>(e - t1 - 1)));
+        if (!parse_i64(t1 + 1, t2 ? t2 : e, start + row)) fail.report("bad start position", row, b, e);
+        chrom_index[row] = ci;
+        ++row;
+      });
+    });
+  for (auto& th : pool) th.join();
+  if (fail.set.load()) {
+    set_error("cgcn_bed_starts_parse(%s): %s", path, fail.msg);
+    return CGCN_ERR_DATA;
+  }
+  *rows_out = off[T];
+  return CGCN_OK;
+}

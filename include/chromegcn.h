@@ -77,6 +77,11 @@ int cgcn_text_count_rows(const char* path, int32_t threads, int64_t* rows_out);
 int cgcn_contacts_parse(const char* path, int64_t capacity, int64_t* bin1, int64_t* bin2, double* val,
                         int64_t* rows_out, int32_t threads);
 int cgcn_vector_parse(const char* path, int64_t capacity, double* out, int64_t* rows_out, int32_t threads);
+/* Windows bed file of create_bin_dict (data/7create_graph_new.py:24-37): for every row whose first column is one of
+ * `chroms` ('\n'-separated names) the index of that name and the row's start position, in file order.  With
+ * capacity too small returns CGCN_ERR_CAPACITY and the number of matching rows in *rows_out. */
+int cgcn_bed_starts_parse(const char* path, const char* chroms, int64_t capacity, int32_t* chrom_index, int64_t* start,
+                          int64_t* rows_out, int32_t threads);
 
 /*
  * Hi-C contact list -> symmetric binary window adjacency in CSR (no self loops).

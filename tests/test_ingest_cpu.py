@@ -93,3 +93,29 @@ def test_malformed_rows_are_reported_with_their_row(tmp_path):
     open(empty, "w").close()
     b1, b2, v = cg.read_contacts(empty)
     assert len(b1) == 0 and len(v) == 0
+
+
+def test_bed_window_starts_match_the_reference_loop(tmp_path, monkeypatch):
+    """create_bin_dict (data/7create_graph_new.py:24-44): unique start positions per requested chromosome, sorted."""
+    rng = np.random.default_rng(3)
+    chroms_in_file = ["chr1", "chr10", "chr2", "chrX", "chr1_gl000191_random"]
+    rows = []
+    for _ in range(60_000):
+        c = chroms_in_file[rng.integers(0, len(chroms_in_file))]
+        s = int(rng.integers(0, 3000)) * 1000
+        rows.append("%s\t%d\t%d\tassay%d\t0\t.\t1.5\t2.0\t3.0\t50" % (c, s, s + 1000, rng.integers(0, 100)))
+    path = str(tmp_path / "chipseq_windows.bed")
+    with open(path, "w") as fp:
+        fp.write("\n".join(rows) + "\n")
+    wanted = ["chr1", "chr2", "chr3", "chrX"]                      # chr3 has no rows; chr10 / the random contig are ignored
+    want = {c: set() for c in wanted}
+    for r in rows:
+        f = r.split("\t")
+        if f[0] in want:
+            want[f[0]].add(int(f[1]))
+    got = cg.read_window_starts(path, wanted)
+    monkeypatch.setenv("CGCN_TEXT_PARSER", "pandas")
+    got_pd = cg.read_window_starts(path, wanted)
+    for c in wanted:
+        assert got[c].dtype == np.int64 and got[c].tolist() == sorted(want[c])
+        assert np.array_equal(got[c], got_pd[c])
