@@ -362,6 +362,7 @@ def main():
                             "achieved can exceed the DRAM copy peak; see profiles/ for dram__bytes"}
 
     cpu_baseline = None
+    hostbind.unbind(binding)       # the CPU baseline gets every host core back (and the JSON line no CPU list)
     if rank == 0 and not args.no_cpu_baseline:
         v, dt_cpu, e_cpu, threads = cpu_reference_run(["chr22"], steps=10, warmup=2)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -33,7 +33,18 @@ def bind_to_gpu(device_index: int) -> Dict:
             info.update(bound=True, cpus=len(target), reason="already local")
         else:
             os.sched_setaffinity(0, target)
-            info.update(bound=True, cpus=len(target), reason="restricted %d -> %d CPUs" % (len(allowed), len(target)))
+            info.update(bound=True, cpus=len(target), reason="restricted %d -> %d CPUs" % (len(allowed), len(target)),
+                        previous=sorted(allowed))
     except Exception as exc:            # no NVML, no permission, ...: run unbound
         info["reason"] = "%s: %s" % (type(exc).__name__, exc)
     return info
+
+
+def unbind(info: Dict) -> None:
+    """Give the process back the CPU set it had before `bind_to_gpu` (for host-only work such as a CPU baseline)."""
+    prev = info.pop("previous", None)
+    if prev:
+        try:
+            os.sched_setaffinity(0, set(prev))
+        except Exception:
+            pass
