@@ -358,8 +358,9 @@ def main():
                     "traffic_source": traffic_src,
                     "peak_source": peak_src, "avg_launch_us": tot_ms * 1e3 / n_launch,
                     "algorithmic_bytes_per_launch": tot_bytes / n_launch,
-                    "note": "algorithmic bytes nnz*(4+4W)+4(N+1)+4WN; Hi-C locality keeps most gathers in L2, so "
-                            "achieved can exceed the DRAM copy peak; see profiles/ for dram__bytes"}
+                    "note": "algorithmic bytes nnz*(4+4W)+4(N+1)+4WN; the launches of one pass run back to back between one "
+                            "CUDA-event pair; Hi-C locality keeps most gathers in L1/L2, so achieved can exceed the DRAM "
+                            "copy peak; see profiles/ for dram__bytes"}
 
     cpu_baseline = None
     hostbind.unbind(binding)       # the CPU baseline gets every host core back (and the JSON line no CPU list)
