@@ -319,49 +319,54 @@ def main():
     # ---- roofline of the dominant kernel: the SpMM, one launch per local chromosome, timed alone with CUDA events
     roofline = None
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-        W = 2 * D
-        outs = {c: torch.empty_like(panels[c]) for c in mine}
-        for _ in range(3):
-            for c in mine:
-                ops.spmm(graphs[c], panels[c].view(graphs[c].n, W), True, out=outs[c].view(graphs[c].n, W))
-        torch.cuda.synchronize(dev)
-        # One event pair around a back-to-back pass over the chromosomes (no host round trip between launches, so the
-        # host's launch latency is not part of the interval); every launch reads a different 50+ MB panel, 1.2 GB in
-        # total per pass, so nothing survives in L2 from one launch to the next.
-        reps, tot_ms, tot_bytes, n_launch = 5, 0.0, 0.0, 0
-        for _ in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for c in mine:
-                ops.spmm(graphs[c], panels[c].view(graphs[c].n, W), True, out=outs[c].view(graphs[c].n, W))
-            b.record()
-            b.synchronize()
-            tot_ms += a.elapsed_time(b)
-            for c in mine:
-                g = graphs[c]
-                tot_bytes += g.nnz * (4 + 4 * W) + 4 * (g.n + 1) + 4 * W * g.n
-                n_launch += 1
-        achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
-        # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01b_spmm_traffic.json")
-        if args.workload == "wg" and world == 1 and os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01b_spmm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches)" % tj["launches"]
-        roofline = {"bound": "hbm", "kernel": "spmm_pattern_kernel<2> (forward mean aggregation, width 256)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": traffic_src,
-                    "peak_source": peak_src, "avg_launch_us": tot_ms * 1e3 / n_launch,
-                    "algorithmic_bytes_per_launch": tot_bytes / n_launch,
-                    "note": "algorithmic bytes nnz*(4+4W)+4(N+1)+4WN; the launches of one pass run back to back between one "
-                            "CUDA-event pair; Hi-C locality keeps most gathers in L1/L2, so achieved can exceed the DRAM "
-                            "copy peak; see profiles/ for dram__bytes"}
+        try:
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(peaks_path):
+                peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+            else:
+                peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+            W = 2 * D
+            outs = {c: torch.empty_like(panels[c]) for c in mine}
+            for _ in range(3):
+                for c in mine:
+                    ops.spmm(graphs[c], panels[c].view(graphs[c].n, W), True, out=outs[c].view(graphs[c].n, W))
+            torch.cuda.synchronize(dev)
+            # One event pair around a back-to-back pass over the chromosomes (no host round trip between launches, so the
+            # host's launch latency is not part of the interval); every launch reads a different 50+ MB panel, 1.2 GB in
+            # total per pass, so nothing survives in L2 from one launch to the next.
+            reps, tot_ms, tot_bytes, n_launch = 5, 0.0, 0.0, 0
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for c in mine:
+                    ops.spmm(graphs[c], panels[c].view(graphs[c].n, W), True, out=outs[c].view(graphs[c].n, W))
+                b.record()
+                b.synchronize()
+                tot_ms += a.elapsed_time(b)
+                for c in mine:
+                    g = graphs[c]
+                    tot_bytes += g.nnz * (4 + 4 * W) + 4 * (g.n + 1) + 4 * W * g.n
+                    n_launch += 1
+            achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+            # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r01b_spmm_traffic.json")
+            if args.workload == "wg" and world == 1 and os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01b_spmm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches)" % tj["launches"]
+            roofline = {"bound": "hbm", "kernel": "spmm_pattern_kernel<2> (forward mean aggregation, width 256)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                        "traffic_source": traffic_src,
+                        "peak_source": peak_src, "avg_launch_us": tot_ms * 1e3 / n_launch,
+                        "algorithmic_bytes_per_launch": tot_bytes / n_launch,
+                        "note": "algorithmic bytes nnz*(4+4W)+4(N+1)+4WN; the launches of one pass run back to back between one "
+                                "CUDA-event pair; Hi-C locality keeps most gathers in L1/L2, so achieved can exceed the DRAM "
+                                "copy peak; see profiles/ for dram__bytes"}
 
+        except Exception as exc:      # rank-0-only, no collective inside: a failure here must not cost the main line
+            import traceback
+            traceback.print_exc()
+            roofline = {"bound": "hbm", "error": "%s: %s" % (type(exc).__name__, exc)}
     cpu_baseline = None
     hostbind.unbind(binding)       # the CPU baseline gets every host core back (and the JSON line no CPU list)
     if rank == 0 and not args.no_cpu_baseline:
