@@ -38,6 +38,16 @@ def padded_classes(nclass: int) -> int:
     return (nclass + 3) // 4 * 4
 
 
+def bn_momentum(bn: nn.BatchNorm1d) -> float:
+    """The exponential factor of the running statistics.  `momentum=None` (cumulative moving average with factor
+    1 / num_batches_tracked) is not what the reference builds (models/ChromeModels.py:30: `nn.BatchNorm1d(nfeat)`)
+    and is not implemented by the kernels: refuse it instead of silently using 0.1."""
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative moving average) is not supported by the "
+                                  "CUDA path; the reference uses the default momentum 0.1")
+    return float(bn.momentum)
+
+
 def _as_graph(adj, cache: Dict) -> HiCGraph:
     if isinstance(adj, HiCGraph):
         return adj
@@ -191,7 +201,7 @@ class _ChromeGCNFn(torch.autograd.Function):
             bn = module.batch_norm
             m = build_model_struct(graph, d, nclass, layers, 1, training, module.dropout, seed, step, params, None,
                                    bn.running_mean, bn.running_var, bn.num_batches_tracked, x, None, out, gates, None, ws,
-                                   module.gemm_impl, bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld,
+                                   module.gemm_impl, bn_momentum(bn), bn.eps, ld,
                                    module.gate_off)
             _lib.check(lib.cgcn_model_forward(C.byref(m)), "cgcn_model_forward")
         ctx.module, ctx.graph, ctx.names = module, graph, names
@@ -220,7 +230,7 @@ class _ChromeGCNFn(torch.autograd.Function):
             bn = module.batch_norm
             m = build_model_struct(graph, d, nclass, layers, 1, training, module.dropout, seed, step, params, grads,
                                    bn.running_mean, bn.running_var, None, x, dx, out, gates, dout, ws, module.gemm_impl,
-                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld, module.gate_off)
+                                   bn_momentum(bn), bn.eps, ld, module.gate_off)
             _lib.check(lib.cgcn_model_backward(C.byref(m)), "cgcn_model_backward")
         return (dx, None, None, *[grads[k] for k in names])
 

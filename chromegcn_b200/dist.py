@@ -123,6 +123,8 @@ def sharded_train_epoch(engine, optimizer, schedule, rank: int, graphs, panels, 
         schedule = [[[s[t]] if t < len(s) else [] for s in shards] for t in range(num_rounds(shards))]
     acc = None
     i = 0
+    bn = engine.model.batch_norm
+    nbt_before = bn.num_batches_tracked.clone() if bn.num_batches_tracked is not None else None
     for rnd in schedule:
         mine = rnd[rank]
         if len(mine) == 0:
@@ -138,18 +140,46 @@ def sharded_train_epoch(engine, optimizer, schedule, rank: int, graphs, panels, 
         if len(mine) > 1:
             fp.flat_grad.copy_(acc)
         allreduce_gradients(fp.flat_grad, group)
-        optimizer.grad_scale = 1.0 / max(sum(len(cell) for cell in rnd), 1)
+        step_on_mean(optimizer, fp.flat_grad, 1.0 / max(sum(len(cell) for cell in rnd), 1))
+    sync_batchnorm_buffers(engine.model, group, nbt_before)
+
+
+def step_on_mean(optimizer, flat_grad: torch.Tensor, scale: float) -> None:
+    """One optimiser step on `scale * flat_grad` (the mean of a round's summed gradients).  The flat-buffer
+    optimisers fold the factor into their kernel (`grad_scale`, restored afterwards so that it never leaks into a
+    later single-GPU `finetune()`); any other `torch.optim.Optimizer` gets the buffer scaled in place."""
+    if hasattr(optimizer, "grad_scale"):
+        prev = optimizer.grad_scale
+        optimizer.grad_scale = scale
+        try:
+            optimizer.step()
+        finally:
+            optimizer.grad_scale = prev
+    else:
+        if scale != 1.0:
+            flat_grad.mul_(scale)
         optimizer.step()
 
 
-def sync_batchnorm_buffers(model, group=None) -> None:
-    """Average BatchNorm running statistics across ranks (each rank saw different chromosomes)."""
+def sync_batchnorm_buffers(model, group=None, nbt_before: torch.Tensor = None) -> None:
+    """Make the BatchNorm running statistics identical on every rank after a chromosome-sharded pass.  The
+    reference updates ONE model's `running_mean / running_var` once per strand call of every chromosome
+    (models/ChromeModels.py:49, finetune.py:41-42); here each rank only saw its own chromosomes, so the replicas end a
+    pass with different buffers and an eval pass or a checkpoint (`utils/evals.py:250-263` saves the whole
+    state_dict) would depend on the rank.  The buffers become the rank average (every rank's exponential average
+    started from the same value and has seen ~1/world of the batches), and `num_batches_tracked` the start value
+    plus the calls of ALL ranks, as in a single-model pass."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     w = dist.get_world_size(group)
-    for buf in (model.batch_norm.running_mean, model.batch_norm.running_var):
+    bn = model.batch_norm
+    for buf in (bn.running_mean, bn.running_var):
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         buf.div_(w)
+    if nbt_before is not None and bn.num_batches_tracked is not None:
+        delta = (bn.num_batches_tracked - nbt_before).to(torch.int64)
+        dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
+        bn.num_batches_tracked.copy_(nbt_before + delta)
 
 
 # ------------------------------------------------------------------ one oversized graph: row partition
@@ -326,7 +356,7 @@ class RowPartitionedStep:
         flat gradient buffer."""
         import ctypes as C
         from . import _lib, ops
-        from .chrome_models import build_model_struct, padded_classes
+        from .chrome_models import bn_momentum, build_model_struct, padded_classes
         from .engine import flat_params
         lib = _lib.load()
         model, eng, S = self.model, self.engine, self.S
@@ -353,7 +383,7 @@ class RowPartitionedStep:
                                    fp.views(fp.flat), fp.views(fp.flat_grad) if train else None, bn.running_mean,
                                    bn.running_var, bn.num_batches_tracked, panel_local, input_grad, out, gates,
                                    dout if train else None, ws, model.gemm_impl,
-                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld,
+                                   bn_momentum(bn), bn.eps, ld,
                                    getattr(model, "gate_off", False))
             m.n_total, m.row_begin = self.n_total, self.parts[self.rank][0]
             m.x_full, m.bn_sums = (None if use_peer else x_full.data_ptr()), bn_sums.data_ptr()

@@ -18,7 +18,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib, ops
-from .chrome_models import ChromeGCN, build_model_struct, padded_classes
+from .chrome_models import ChromeGCN, bn_momentum, build_model_struct, padded_classes
 from .graph import HiCGraph
 
 _SLOT = 64  # floats: every parameter starts on a 256-byte boundary inside the flat buffer
@@ -158,7 +158,7 @@ class ChromosomeEngine:
             m = build_model_struct(graph, d, nclass, layers, S, model.training, model.dropout, seed, step, params,
                                    grads if train else None, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                                    panel, input_grad, out, gates, None, ws, model.gemm_impl,
-                                   bn.momentum if bn.momentum is not None else 0.1, bn.eps, ld,
+                                   bn_momentum(bn), bn.eps, ld,
                                    getattr(model, "gate_off", False))
             bits = target.dtype == torch.int32            # ops.pack_targets bit rows
             if bits:

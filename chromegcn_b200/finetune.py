@@ -26,7 +26,7 @@ from .graph import HiCGraph, process_graph
 _GRAPH_FILES: Dict = {}      # (path, mtime, device) -> {chrom: scipy csr}
 _GRAPHS: Dict = {}           # (path, mtime, device, adj_type, chrom, n) -> HiCGraph
 _ENGINES: Dict = {}          # id(model) -> ChromosomeEngine
-_RESIDENT: Dict = {}         # (id(dict), chrom, device) -> (panel, target)
+_RESIDENT: Dict = {}         # (id(dict), chrom, device) -> (signature of the host tensors, panel, target)
 
 
 def clear_caches() -> None:
@@ -38,6 +38,26 @@ def clear_caches() -> None:
     _STAGING.clear()
     _PACKED.clear()
     DEVICE_OUTPUTS.clear()
+
+
+def _feature_signature(feats) -> tuple:
+    """Identity of one chromosome's host tensors: object (weak reference), storage address, shape and in-place
+    version of each.  A `_RESIDENT` entry is only reused while this is unchanged, so a new dict that happens to get a
+    freed dict's `id()` (a second `run_model`, cross-validation folds) or features edited in place are re-uploaded."""
+    import weakref
+    sig = []
+    for k in ("forward", "backward", "target"):
+        t = feats[k]
+        sig.append((weakref.ref(t), t.data_ptr(), tuple(t.shape), t._version))
+    return tuple(sig)
+
+
+def _signature_matches(sig, feats) -> bool:
+    for (ref, ptr, shape, version), k in zip(sig, ("forward", "backward", "target")):
+        t = feats[k]
+        if ref() is not t or t.data_ptr() != ptr or tuple(t.shape) != shape or t._version != version:
+            return False
+    return True
 
 
 def engine_for(model) -> ChromosomeEngine:
@@ -172,6 +192,14 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
             offsets.append(offsets[-1] + sizes[c])
         all_preds = torch.empty(total_rows, nclass, dtype=torch.float32, pin_memory=True)
         losses_dev = torch.zeros(max(len(chroms), 1), dtype=torch.float32, device=device)
+        # the copy streams write into buffers allocated (possibly from recycled blocks) under the compute stream:
+        # order them after everything the compute stream has been given so far, and tell the allocator who else
+        # touches them
+        h2d.wait_stream(main)
+        d2h.wait_stream(main)
+        if all_tbits_dev is not None:
+            all_tbits_dev.record_stream(h2d)
+        all_preds_dev.record_stream(d2h)
         staged = [None, None]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -183,8 +211,10 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
             feats = chrom_feature_dict[chrom]
             rkey = (id(chrom_feature_dict), chrom, str(device))
             if resident and rkey in _RESIDENT:
-                staged[k % 2] = ("resident",) + _RESIDENT[rkey]
-                return
+                if _signature_matches(_RESIDENT[rkey][0], feats):
+                    staged[k % 2] = ("resident",) + _RESIDENT[rkey][1:]
+                    return
+                del _RESIDENT[rkey]                              # stale: another dict / edited features
             n, d = feats["forward"].shape
             x_f, x_r, tgt = _staging(device, k % 2, n, d, nclass)
             if all_bits:
@@ -214,7 +244,8 @@ def finetune(WindowModel, ChromeModel, chrom_feature_dict, crit, optimizer, epoc
                 if resident:
                     panel = ops.interleave_strands([x_f, x_r])
                     tgt = tgt.clone()
-                    _RESIDENT[(id(chrom_feature_dict), chrom, str(device))] = (panel, tgt)
+                    _RESIDENT[(id(chrom_feature_dict), chrom, str(device))] = (
+                        _feature_signature(chrom_feature_dict[chrom]), panel, tgt)
                 else:
                     panel = engine.pack(x_f, x_r)
             if train:

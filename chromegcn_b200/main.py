@@ -30,6 +30,10 @@ def main(argv=None):
     opt.tgt_vocab_size = nclass
     model = ChromeGCN(128, 128, nclass, opt.gcn_dropout, opt.gate, opt.gcn_layers)       # main.py:62
     ckpt = os.path.join(opt.model_name.replace('.load_gcn', ''), 'model.chkpt') if opt.load_gcn else os.path.join(base, 'model.chkpt')
+    if not os.path.exists(ckpt) and not os.environ.get('CHROMEGCN_RANDOM_HEAD_INIT'):
+        # main.py:66-73 loads unconditionally (torch.load raises); training on a random head is opt-in only
+        raise FileNotFoundError("%s: the %s checkpoint is required (set CHROMEGCN_RANDOM_HEAD_INIT=1 to train from a "
+                                "random head instead)" % (ckpt, 'GCN' if opt.load_gcn else 'CNN'))
     if os.path.exists(ckpt):
         sd = torch.load(ckpt, weights_only=False)['model']
         if opt.load_gcn:

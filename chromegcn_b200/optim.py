@@ -28,10 +28,14 @@ class _FlatOptimizer(torch.optim.Optimizer):
         return b
 
     def zero_grad(self, set_to_none: bool = True):
-        # the fused backward overwrites (never accumulates into) every gradient, so there is nothing to
-        # clear on the hot path; an explicit zero_grad(set_to_none=False) still zeroes the flat buffer
-        if not set_to_none:
-            flat_params(self.model, full=False).flat_grad.zero_()
+        """Always clears the flat gradient buffer (one ~190 KB memset).  Every `p.grad` is a view into it, so
+        `set_to_none` cannot detach them without breaking the one-kernel step; zeroing is what makes the
+        reference's own loop (`zero_grad(); loss.backward(); step()`, finetune.py:39-49) correct when the
+        gradients come from autograd (`_ChromeGCNFn`), whose AccumulateGrad nodes add into `p.grad` in place.
+        The fused `cgcn_train_step` overwrites the buffer anyway."""
+        fp = flat_params(self.model, full=False)
+        fp.flat_grad.zero_()
+        fp.attach_grads()
 
     def state_dict(self):
         sd = super().state_dict()

@@ -41,33 +41,52 @@ def run_epoch(WindowModel, ChromeModel, split_data, crit, optimizer, epoch, data
 
 
 class SaveLogger:
-    """utils/evals.py:265-300 (log lines) + :250-263 (best-checkpoint rule)."""
+    """utils/evals.py:265-300: empty log files (no header line), `best_loss_epoch` = epoch of the lowest validation
+    loss with its `epochs/best_*_loss.pt` predictions, `epochs/best_*_metrics.pt` for the best validation metric sum,
+    and the `save_mode == 'best'` checkpoint rule of `save_model` (:250-263)."""
 
     def __init__(self, model_name):
         self.model_name = model_name
+        self.best_valid_loss = float("inf")
+        self.best_valid_metric = 0
         self.best_loss_epoch = 0
-        os.makedirs(model_name, exist_ok=True)
+        os.makedirs(os.path.join(model_name, "epochs"), exist_ok=True)
         for f in ("train.log", "valid.log", "test.log"):
-            with open(os.path.join(model_name, f), "w") as fp:
-                fp.write("epoch,loss,mAP,meanAUC,meanAUPR,meanFDR\n")
+            open(os.path.join(model_name, f), "w").close()
 
     def log(self, file_name, epoch, loss, metrics):
         if metrics is None:
             return
         with open(os.path.join(self.model_name, file_name), "a") as fp:
-            fp.write("%d,%s,%s,%s,%s,%s\n" % (epoch, loss, metrics.get("mAP", 0), metrics["meanAUC"], metrics["meanAUPR"],
+            fp.write("%s,%s,%s,%s,%s,%s\n" % (epoch, loss, metrics.get("mAP", 0), metrics["meanAUC"], metrics["meanAUPR"],
                                               metrics["meanFDR"]))
 
-    def save(self, epoch, opt, ChromeModel, valid_metrics_sum, valid_metrics_sums, valid_preds, valid_targs, test_preds,
-             test_targs):
-        if valid_metrics_sums and valid_metrics_sum >= max(valid_metrics_sums):
+    def _dump(self, tag, valid_preds, valid_targs, test_preds, test_targs):
+        d = os.path.join(self.model_name, "epochs")
+        torch.save(valid_preds, os.path.join(d, "best_valid_preds_%s.pt" % tag))
+        torch.save(valid_targs, os.path.join(d, "best_valid_targets_%s.pt" % tag))
+        torch.save(test_preds, os.path.join(d, "best_test_preds_%s.pt" % tag))
+        torch.save(test_targs, os.path.join(d, "best_test_targets_%s.pt" % tag))
+
+    def save(self, epoch, opt, ChromeModel, valid_loss, valid_metrics_sum, valid_metrics_sums, valid_preds, valid_targs,
+             test_preds, test_targs):
+        if valid_loss < self.best_valid_loss:                                  # utils/evals.py:276-283
+            self.best_valid_loss = valid_loss
             self.best_loss_epoch = epoch
-            torch.save({"model": ChromeModel.state_dict(), "settings": opt, "epoch": epoch},
-                       os.path.join(self.model_name, "model.chkpt"))
-            torch.save(valid_preds, os.path.join(self.model_name, "best_valid_preds.pt"))
-            torch.save(valid_targs, os.path.join(self.model_name, "best_valid_targets.pt"))
-            torch.save(test_preds, os.path.join(self.model_name, "best_test_preds.pt"))
-            torch.save(test_targs, os.path.join(self.model_name, "best_test_targets.pt"))
+            self._dump("loss", valid_preds, valid_targs, test_preds, test_targs)
+        if valid_metrics_sum > self.best_valid_metric:                         # :284-289
+            self.best_valid_metric = valid_metrics_sum
+            self._dump("metrics", valid_preds, valid_targs, test_preds, test_targs)
+        # :291 (`not 'test' in self.model_name`: the reference tests the whole path string; only the run's own
+        # directory name is examined here, so that a parent directory called e.g. "tests" does not disable saving)
+        if "test" in os.path.basename(os.path.normpath(self.model_name)) or getattr(opt, "test_only", False):
+            return
+        ckpt = {"model": ChromeModel.state_dict(), "settings": opt, "epoch": epoch}
+        if getattr(opt, "save_mode", "best") == "all":                         # :253-255
+            torch.save(ckpt, os.path.join(self.model_name, "accu_{accu:3.3f}.chkpt".format(accu=100 * valid_metrics_sum)))
+        elif valid_metrics_sums and valid_metrics_sum >= max(valid_metrics_sums):
+            torch.save(ckpt, os.path.join(self.model_name, "model.chkpt"))
+            print("[Info] The checkpoint file has been updated.")
 
 
 def run_model(WindowModel, ChromeModel, train_data, valid_data, test_data, crit, optimizer, scheduler, opt, data_dict, logger):
@@ -95,8 +114,8 @@ def run_model(WindowModel, ChromeModel, train_data, valid_data, test_data, crit,
         test_metrics = compute_metrics(test_preds, test_targs, test_loss, opt, elpsd, data_dict, opt.cell_type, "test")
         if logger is not None:
             logger.evaluate(train_metrics, valid_metrics, test_metrics, epoch, getattr(opt, "total_num_parameters", 0))
-        save_logger.save(epoch, opt, ChromeModel, valid_metrics_sum, valid_metrics_sums, valid_preds, valid_targs, test_preds,
-                         test_targs)
+        save_logger.save(epoch, opt, ChromeModel, valid_loss, valid_metrics_sum, valid_metrics_sums, valid_preds, valid_targs,
+                         test_preds, test_targs)
         save_logger.log("test.log", epoch, test_loss, test_metrics)
         save_logger.log("valid.log", epoch, valid_loss, valid_metrics)
         save_logger.log("train.log", epoch, train_loss, train_metrics)

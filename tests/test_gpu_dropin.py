@@ -84,7 +84,9 @@ def test_run_model_two_epochs(tmp_path):
     ck = torch.load(tmp_path / "model" / "model.chkpt", weights_only=False)
     assert set(ck) == {"model", "settings", "epoch"} and "GC1.weight" in ck["model"]
     lines = open(tmp_path / "model" / "train.log").read().strip().splitlines()
-    assert lines[0] == "epoch,loss,mAP,meanAUC,meanAUPR,meanFDR" and len(lines) == 4
+    assert len(lines) == 3 and lines[0].startswith("1,") and len(lines[0].split(",")) == 6     # utils/evals.py:297-300: no header
+    assert os.path.exists(tmp_path / "model" / "epochs" / "best_valid_preds_loss.pt")           # utils/evals.py:279-282
+    assert os.path.exists(tmp_path / "model" / "epochs" / "best_test_targets_metrics.pt")      # :286-289
     # the checkpoint loads into the CPU oracle (== the reference's class layout)
     from oracle.gcn import ChromeGCNOracle
     ChromeGCNOracle(128, 128, nclass, 0.2, True, 2).load_state_dict(ck["model"])
@@ -101,8 +103,9 @@ def test_run_model_two_epochs(tmp_path):
     for a, b in zip(hist, hist2):
         assert a["train_loss"] == b["train_loss"] and a["test_loss"] == b["test_loss"]
         assert abs(a["test_meanAUC"] - b["test_meanAUC"]) <= 1e-9 and abs(a["test_meanAUPR"] - b["test_meanAUPR"]) <= 1e-9
-    dev_log = open(tmp_path / "model" / "test.log").read().strip().splitlines()[1:]
-    host_log = open(tmp_path / "model_host_metrics" / "test.log").read().strip().splitlines()[1:]
+    dev_log = open(tmp_path / "model" / "test.log").read().strip().splitlines()
+    host_log = open(tmp_path / "model_host_metrics" / "test.log").read().strip().splitlines()
+    assert len(dev_log) == 3
     for la, lb in zip(dev_log, host_log):
         va, vb = [float(x) for x in la.split(",")], [float(x) for x in lb.split(",")]
         assert max(abs(x - y) for x, y in zip(va, vb)) <= 1e-9
