@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libchromegcn.so")
-SOURCES = ["spmm.cu", "gemm_ffma.cu", "gemm_tc.cu", "rowwise.cu", "adjacency.cu", "metrics.cu", "ingest.cu", "model.cu"]
+SOURCES = ["spmm.cu", "fused_layer.cu", "gemm_ffma.cu", "gemm_tc.cu", "rowwise.cu", "adjacency.cu", "metrics.cu", "ingest.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-pthread", "--expt-relaxed-constexpr", "-cudart", "static"]
 

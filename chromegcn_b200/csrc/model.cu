@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "fused_layer.cuh"
 #include "rowwise_args.cuh"
 
 namespace cgcn {
@@ -349,6 +350,14 @@ static bool use_images(const cgcn_model* m) {
 static const void* fwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.ws + c.lay.img_fwd[i] : nullptr; }
 static const void* bwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.ws + c.lay.img_bwd[i] : nullptr; }
 
+// The fused layer kernels (fused_layer.cu): one launch per layer and direction instead of SpMM + contraction + gate
+// kernel.  In this mode the saved `ax` panels hold the UN-normalised neighbour sums and the `dy` panels hold
+// D^-1 dy, so that d W = ax^T dy is unchanged while the backward gather needs no per-neighbour scale.
+static bool use_fused(const cgcn_model* m) {
+  static const bool off = getenv("CGCN_NO_FUSED") != nullptr;       // developer aid / A-B measurements
+  return !off && use_images(m) && fused_layer_supported(m->d, &m->graph) && m->peer == nullptr;
+}
+
 static int prep_fwd_images(const Ctx& c) {
   pdl_plain_next(c.st);              // first kernel of a pass: ordinary stream order against whatever ran before
   if (!use_images(c.m)) return CGCN_OK;
@@ -368,6 +377,22 @@ static int prep_bwd_images(const Ctx& c) {
   return tc_prep_images(sp, k, c.st);
 }
 
+// BatchNorm statistics from the last layer's per-CTA column sums (`parts` partial rows in lay.partial)
+static int fwd_layer_stats(const Ctx& c, bool last, int parts) {
+  const cgcn_model* m = c.m;
+  const WsLayout& lay = c.lay;
+  float* ws = c.ws;
+  if (!last) return CGCN_OK;
+  if (c.dist && m->training)         // publish this rank's column sums; the host all-reduces m->bn_sums
+    return bn_finalize_launch(ws + lay.partial, parts, c.n_total, c.S, c.d, m->bn_eps, m->bn_momentum, 1, m->bn_running_mean,
+                              m->bn_running_var, nullptr, ws + lay.bn_mean, ws + lay.bn_rstd, nullptr, m->bn_sums, c.st);
+  if (!c.dist)
+    return bn_finalize_launch(ws + lay.partial, parts, c.n, c.S, c.d, m->bn_eps, m->bn_momentum, m->training,
+                              m->bn_running_mean, m->bn_running_var, m->bn_num_batches_tracked, ws + lay.bn_mean,
+                              ws + lay.bn_rstd, nullptr, nullptr, c.st);
+  return CGCN_OK;
+}
+
 // layer l: ax = A_hat x ; y = ax W + b ; gate.  `gather_src` is the panel the SpMM reads neighbours from (the
 // layer input itself on one GPU, the all-gathered copy of it when row-partitioned).
 static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
@@ -375,6 +400,31 @@ static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
   const WsLayout& lay = c.lay;
   float* ws = c.ws;
   const float* xin = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
+  const bool last = (l == c.L - 1);
+  int grid = 0;
+  if (use_fused(m)) {
+    // gather -> (A_hat x) W + b -> tanh -> gate -> blend -> dropout (-> BatchNorm column sums) in one kernel
+    fl::Args a{};
+    a.rowptr = m->graph.rowptr;
+    a.colidx = m->graph.colidx;
+    a.n = c.n;
+    a.gsrc = gather_src;
+    a.w = m->params.gc_w[l];
+    a.w_transposed = 0;
+    a.xin = xin;
+    a.bias = m->params.gc_b[l];
+    a.wg = m->params.gate_w[l];
+    a.bg = m->params.gate_b[l];
+    a.sx = ws + lay.ax[l];
+    a.z = ws + lay.z[l];
+    a.xo = ws + lay.xo[l];
+    a.g = m->gate[l];
+    a.partial = ws + lay.partial;
+    a.gate_off = m->gate_off;
+    a.drop = make_dropout(m->dropout_p, m->seed, m->step, layer_drop_site(l), m->training && !last, c.drop_off);
+    CGCN_TRY(fused_layer_launch(a, c.S, (last && m->training) ? fl::FWD_STATS : fl::FWD, &grid, c.st));
+    return fwd_layer_stats(c, last, grid);
+  }
   // ax = A_hat x                                   (torch.spmm, models/SubLayers.py:46)
   if (c.dist && m->peer != nullptr)  // neighbour rows straight from the owners' exchange buffers (NVLink loads)
     CGCN_TRY(spmm_peer_launch(&m->graph, m->peer, ws + lay.ax[l], c.W, 1, nullptr, c.st));
@@ -396,20 +446,9 @@ static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
   a.stats_partial = ws + lay.partial;
   a.n = c.n;
   a.gate_off = m->gate_off;
-  const bool last = (l == c.L - 1);
   a.drop = make_dropout(m->dropout_p, m->seed, m->step, layer_drop_site(l), m->training && !last, c.drop_off);
-  int grid = 0;
   CGCN_TRY(gate_fwd_launch(a, c.d, c.S, last && m->training, &grid, c.st));
-  if (last) {
-    if (c.dist && m->training)       // publish this rank's column sums; the host all-reduces m->bn_sums
-      CGCN_TRY(bn_finalize_launch(ws + lay.partial, grid, c.n_total, c.S, c.d, m->bn_eps, m->bn_momentum, 1, m->bn_running_mean,
-                                  m->bn_running_var, nullptr, ws + lay.bn_mean, ws + lay.bn_rstd, nullptr, m->bn_sums, c.st));
-    else if (!c.dist)
-      CGCN_TRY(bn_finalize_launch(ws + lay.partial, grid, c.n, c.S, c.d, m->bn_eps, m->bn_momentum, m->training,
-                                  m->bn_running_mean, m->bn_running_var, m->bn_num_batches_tracked, ws + lay.bn_mean,
-                                  ws + lay.bn_rstd, nullptr, nullptr, c.st));
-  }
-  return CGCN_OK;
+  return fwd_layer_stats(c, last, grid);
 }
 
 static int fwd_head(const Ctx& c) {
@@ -529,6 +568,84 @@ static int bwd_propagate(const Ctx& c, int l_from, const float* t_gather) {
   return spmm_launch(&c.m->graph, t_gather, dx, c.W, 0, c.ws + c.lay.dC, c.st);
 }
 
+// ---- fused backward (use_fused): the gather comes first, A_hat^T G W^T = (P (D^-1 G)) W^T.
+// Gradient entering layer l_from - 1 from layer l_from: one kernel gathers u = P dys_{l_from}, contracts u W^T, adds
+// (1-g) dh (dC) and, for l_from > 0, runs the whole gate / tanh backward of layer l_from - 1 in its epilogue (writes
+// dys_{l_from-1}, dC, the column partials; *parts = partial rows written).  l_from == 0: d loss / d x_in.
+static int bwd_propagate_fused(const Ctx& c, int l_from, const float* gather_src, int* parts) {
+  const cgcn_model* m = c.m;
+  const WsLayout& lay = c.lay;
+  float* ws = c.ws;
+  fl::Args a{};
+  a.rowptr = m->graph.rowptr;
+  a.colidx = m->graph.colidx;
+  a.n = c.n;
+  a.gsrc = gather_src;
+  a.w = m->params.gc_w[l_from];
+  a.w_transposed = 1;
+  a.dxd_in = ws + lay.dC;
+  a.gate_off = m->gate_off;
+  if (l_from == 0) {
+    a.dx_out = m->x_in_grad;
+    a.drop = make_dropout(0.f, 0, 0, 0, false, 0);
+    return fused_layer_launch(a, c.S, fl::BWD_INPUT, parts, c.st);
+  }
+  const int lp = l_from - 1;
+  a.wg = m->params.gate_w[lp];
+  a.z_prev = ws + lay.z[lp];
+  a.x_prev = (lp == 0) ? m->x_in : ws + lay.xo[lp - 1];
+  a.g_prev = m->gate[lp];
+  a.dys_out = ws + lay.dy[lp];
+  a.dxd_out = (lp > 0 || m->need_input_grad) ? ws + lay.dC : nullptr;
+  a.partial = ws + lay.partial_l[lp];
+  a.drop = make_dropout(m->dropout_p, m->seed, m->step, layer_drop_site(lp), m->training, c.drop_off);
+  return fused_layer_launch(a, c.S, fl::BWD_MID, parts, c.st);
+}
+
+// Layer l in fused mode.  Head layer: BatchNorm / ReLU / gate backward as a row-wise kernel that stores D^-1 dy.
+// Other layers: their gate stage already ran in the epilogue of bwd_propagate_fused(l + 1) (`parts` partial rows).
+// Then, on the side stream: bias / gate gradients from the partials and d W = ax^T dys.  *t_out = the panel the next
+// propagate gathers (NULL if the chain stops here).
+static int bwd_layer_fused(const Ctx& c, Fork& f, int l, int parts, const float** t_out) {
+  const cgcn_model* m = c.m;
+  const WsLayout& lay = c.lay;
+  float* ws = c.ws;
+  const bool head = (l == c.L - 1);
+  const bool need_dx = (l > 0) || m->need_input_grad;
+  float* dy = ws + lay.dy[l];
+  *t_out = nullptr;
+  if (head) {
+    if (c.dist)                      // c1, c2 from the all-reduced BatchNorm backward sums
+      CGCN_TRY(bn_bwd_finalize_launch(ws + lay.partial, 0, c.n_total, c.S, c.d, m->training, ws + lay.bn_c1, ws + lay.bn_c2, nullptr,
+                                      nullptr, m->bn_sums, nullptr, c.st));
+    GateBwdArgs a{};
+    a.dsrc = bwd_src(c, l);
+    a.h = ws + lay.xo[l];
+    a.mean = ws + lay.bn_mean;
+    a.rstd = ws + lay.bn_rstd;
+    a.gamma = m->params.bn_w;
+    a.c1 = ws + lay.bn_c1;
+    a.c2 = ws + lay.bn_c2;
+    a.z = ws + lay.z[l];
+    a.x = (l == 0) ? m->x_in : ws + lay.xo[l - 1];
+    a.g = m->gate[l];
+    a.wg = m->params.gate_w[l];
+    a.dy = dy;
+    a.dxd = need_dx ? ws + lay.dC : nullptr;
+    a.partial = ws + lay.partial_l[l];
+    a.n = c.n;
+    a.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training, c.drop_off);
+    a.scale_rowptr = m->graph.rowptr;
+    CGCN_TRY(gate_bwd_launch(a, c.d, c.S, true, &parts, c.st));
+  }
+  CGCN_TRY(f.fork());
+  CGCN_TRY(gate_bwd_finalize_launch(ws + lay.partial_l[l], parts, c.d, m->grads.gc_b[l], m->grads.gate_w[l], m->grads.gate_b[l], f.ss));
+  CGCN_TRY(gemm_gram_dispatch(ws + lay.ax[l], c.d, dy, c.d, m->grads.gc_w[l], c.d, c.M, c.d, c.d, 0, m->gemm_impl, ws + lay.gram,
+                              lay.gram_bytes, f.ss));
+  if (need_dx) *t_out = dy;
+  return CGCN_OK;
+}
+
 // gate stage of layer l, its weight gradients (side stream) and, if anything upstream needs it, t = D^-1 (dy W^T).
 // Returns in *t_out the panel holding t (NULL if the chain stops here).
 static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out) {
@@ -582,6 +699,16 @@ static int model_backward(const cgcn_model* m) {
   Fork f;
   CGCN_TRY(make_fork(c, &f));
   CGCN_TRY(bwd_head(c, f));
+  if (use_fused(m)) {
+    int parts = 0;
+    for (int l = c.L - 1; l >= 0; --l) {
+      const float* t = nullptr;
+      CGCN_TRY(bwd_layer_fused(c, f, l, parts, &t));
+      if (t == nullptr) break;
+      CGCN_TRY(bwd_propagate_fused(c, l, t, &parts));      // also the gate stage of layer l - 1
+    }
+    return f.join();
+  }
   for (int l = c.L - 1; l >= 0; --l) {
     const float* t = nullptr;
     CGCN_TRY(bwd_layer(c, f, l, &t));
@@ -619,12 +746,19 @@ static int model_phase(const cgcn_model* m, int kind, int layer, const float** p
     case CGCN_PHASE_BWD_HEAD:
       return bwd_head(c, f);
     case CGCN_PHASE_BWD_LAYER:       // layer == L-1: bn_sums all-reduced ; else: x_full holds the gathered t of layer+1
-      if (layer < c.L - 1) CGCN_TRY(bwd_propagate(c, layer + 1, m->x_full));
-      CGCN_TRY(bwd_layer(c, f, layer, &t));
+      if (use_fused(m)) {
+        int parts = 0;
+        if (layer < c.L - 1) CGCN_TRY(bwd_propagate_fused(c, layer + 1, m->x_full, &parts));
+        CGCN_TRY(bwd_layer_fused(c, f, layer, parts, &t));
+      } else {
+        if (layer < c.L - 1) CGCN_TRY(bwd_propagate(c, layer + 1, m->x_full));
+        CGCN_TRY(bwd_layer(c, f, layer, &t));
+      }
       if (publish) *publish = t;
       return CGCN_OK;
     case CGCN_PHASE_BWD_INPUT:       // x_full holds the gathered t of layer 0
       CGCN_REQUIRE(m->need_input_grad && m->x_in_grad, "cgcn_model_phase: BWD_INPUT without need_input_grad");
+      if (use_fused(m)) return bwd_propagate_fused(c, 0, m->x_full, nullptr);
       return bwd_propagate(c, 0, m->x_full);
     default:
       set_error("cgcn_model_phase: unknown phase %d", kind);

@@ -456,13 +456,14 @@ __global__ void __launch_bounds__(RW_THREADS, (DV == 1) ? 3 : 1) gate_bwd_kernel
       const float g = __ldg(a.g + static_cast<size_t>(row) * S + s);
       const float dgp = part * g * (1.0f - g);
       const float omg = 1.0f - g;
+      const float inv = a.scale_rowptr != nullptr ? inv_degree(a.scale_rowptr, row) : 1.0f;
 #pragma unroll
       for (int v = 0; v < DV; ++v) {
         const float4 dz = make_float4(g * dh[v].x + dgp * wg[v].x, g * dh[v].y + dgp * wg[v].y,
                                       g * dh[v].z + dgp * wg[v].z, g * dh[v].w + dgp * wg[v].w);
         const float4 dy = make_float4(dz.x * (1.0f - z[v].x * z[v].x), dz.y * (1.0f - z[v].y * z[v].y),
                                       dz.z * (1.0f - z[v].z * z[v].z), dz.w * (1.0f - z[v].w * z[v].w));
-        st4(a.dy + base + v * 128, dy);
+        st4(a.dy + base + v * 128, make_float4(dy.x * inv, dy.y * inv, dy.z * inv, dy.w * inv));
         if (a.dxd != nullptr)
           st4(a.dxd + base + v * 128, make_float4(omg * dh[v].x, omg * dh[v].y, omg * dh[v].z, omg * dh[v].w));
         add4(db[v], dy);

@@ -56,6 +56,8 @@ struct GateBwdArgs {
   float* partial;      // [grid][2*D + 4]: sum dy | sum dgp*z | sum dgp
   int n;
   DropoutCfg drop;     // HEAD: site 1 ; MID: site 0
+  const int32_t* scale_rowptr;   // non-NULL: dy is stored as D^-1 dy (1/deg of the window row from this rowptr), the form
+                                 // the fused backward layer kernel gathers; the d b column sums stay un-scaled
 };
 
 }  // namespace cgcn
