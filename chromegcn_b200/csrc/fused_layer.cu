@@ -81,6 +81,25 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// acc += v as two packed fp32x2 adds (FADD2, sm_100): same rounding as four FADDs, half the issue slots
+__device__ __forceinline__ void add4_packed(float4& acc, const float4 v) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, va, vb;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rb, {%2, %3};\n\t"
+      "mov.b64 va, {%4, %5};\n\t"
+      "mov.b64 vb, {%6, %7};\n\t"
+      "add.rn.f32x2 ra, ra, va;\n\t"
+      "add.rn.f32x2 rb, rb, vb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t"
+      "mov.b64 {%2, %3}, rb;\n\t"
+      "}"
+      : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
+      : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -213,12 +232,7 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
       for (int u = 0; u < U; ++u) {
         if (k0 + u < cnt) {
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            acc[s].x += v[u][s].x;
-            acc[s].y += v[u][s].y;
-            acc[s].z += v[u][s].z;
-            acc[s].w += v[u][s].w;
-          }
+          for (int s = 0; s < S; ++s) add4_packed(acc[s], v[u][s]);
         }
       }
     };
@@ -357,6 +371,27 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
         const int64_t grow = tile_prow0 + pr;      // panel row (local)
         const bool valid = grow < prow_end;
         const size_t gofs = static_cast<size_t>(grow) * 128 + 4 * q;
+        {
+          // L1 prefetch of the NEXT step's streamed operands (next 4 rows of this warp; the first 4 of the next tile
+          // after the last step): the epilogue warps have no registers to spare for a software pipeline, and without
+          // this every step starts with a full L2 / DRAM round trip (3 panels in the backward mode).
+          const int64_t nrow_p = (it < 3) ? grow + 4 : grow + (TM - 12);
+          if (nrow_p < prow_end) {
+            const size_t nofs = static_cast<size_t>(nrow_p) * 128 + 4 * q;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              if constexpr (FORWARD) {
+                prefetch_l1(a.xin + nofs + cc * 32);
+              } else {
+                prefetch_l1(a.dxd_in + nofs + cc * 32);
+                if constexpr (MODE == BWD_MID) {
+                  prefetch_l1(a.z_prev + nofs + cc * 32);
+                  prefetch_l1(a.x_prev + nofs + cc * 32);
+                }
+              }
+            }
+          }
+        }
         float4 y[4];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) y[cc] = lds_f4(sY + pr * 512 + (cc * 32 + 4 * q) * 4);
@@ -407,6 +442,14 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
         } else {                                   // BWD_MID: gate / tanh backward of layer l-1 on dx = u W^T + (1-g_l) dh_l
           float4 zv[4];
           float part = 0.f;
+          // scalar operands of the row first: their latency overlaps the panel loads instead of following the reduction
+          float g = 1.0f;
+          int deg = 1;
+          if (valid) {
+            if (!a.gate_off) g = __ldg(a.g_prev + grow);
+            const int wr = static_cast<int>(grow / S);
+            deg = __ldg(a.rowptr + wr + 1) - __ldg(a.rowptr + wr);
+          }
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f), xv = e;
@@ -428,10 +471,9 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
           part += __shfl_xor_sync(0xffffffffu, part, 2);
           part += __shfl_xor_sync(0xffffffffu, part, 4);
           if (valid) {
-            const float g = a.gate_off ? 1.0f : __ldg(a.g_prev + grow);
             const float dgp = a.gate_off ? 0.0f : part * g * (1.0f - g);
             const float omg = 1.0f - g;
-            const float inv = inv_degree(a.rowptr, static_cast<int>(grow / S));
+            const float inv = deg > 0 ? __fdiv_rn(1.0f, static_cast<float>(deg)) : 0.0f;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
               const float4 w = lds_f4(sVec1 + (cc * 32 + 4 * q) * 4);
