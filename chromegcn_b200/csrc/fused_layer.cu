@@ -108,7 +108,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
 }
 
-template <int S, int MODE, int G_WARPS>
+template <int S, int MODE, int G_WARPS, bool PEER>
 __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -222,7 +222,15 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int c = __shfl_sync(0xffffffffu, cols, min(k0 + u, last));
-        const float* p = gbase + static_cast<size_t>(c) * (S * 128);
+        const float* p;
+        if constexpr (PEER) {                      // owner of global row c: NVLink load from its exchange buffer
+          int o = 0;
+#pragma unroll
+          for (int r = 1; r < CGCN_MAX_PEERS; ++r) o += (r < a.peer_world && c >= a.peer_begin[r]) ? 1 : 0;
+          p = a.peer_base[o] + static_cast<size_t>(c - a.peer_begin[o]) * (S * 128) + lane * 4;
+        } else {
+          p = gbase + static_cast<size_t>(c) * (S * 128);
+        }
 #pragma unroll
         for (int s = 0; s < S; ++s) v[u][s] = ldg4(p + s * 128);
       }
@@ -567,7 +575,7 @@ int fused_layer_grid(int n, int S, int* rows_per_cta_out) {
 bool fused_layer_supported(int d, const cgcn_graph* g) { return d == 128 && g != nullptr && g->vals == nullptr; }
 
 int fused_layer_launch(fl::Args a, int S, int mode, int* grid_out, cudaStream_t stream) {
-  CGCN_REQUIRE(a.rowptr && a.colidx && a.gsrc && a.w, "fused layer: null graph / panel / weight");
+  CGCN_REQUIRE(a.rowptr && a.colidx && (a.gsrc || a.peer_world > 0) && a.w, "fused layer: null graph / panel / weight");
   CGCN_REQUIRE(S == 1 || S == 2, "fused layer: strands=%d", S);
   int rows = 0;
   const int grid = fused_layer_grid(a.n, S, &rows);
@@ -575,14 +583,17 @@ int fused_layer_launch(fl::Args a, int S, int mode, int* grid_out, cudaStream_t 
   if (grid_out) *grid_out = grid;
   if (a.n <= 0) return CGCN_OK;
   static const int gw = (getenv("CGCN_FUSED_GW") != nullptr && atoi(getenv("CGCN_FUSED_GW")) == 8) ? 8 : 16;
-#define FL_CASE_G(SV, MV, GV)                                                                                        \
-  if (S == SV && mode == MV && gw == GV) {                                                                           \
+  const bool peer = a.peer_world > 0;
+  if (peer) a.gsrc = a.peer_base[0];
+#define FL_CASE_P(SV, MV, GV, PV)                                                                                    \
+  if (S == SV && mode == MV && gw == GV && peer == PV) {                                                             \
     static bool attr_set[64] = {};                                                                                   \
     if (first_use_on_device(attr_set))                                                                               \
-      CGCN_CUDA(cudaFuncSetAttribute(fl::fused_layer_kernel<SV, MV, GV>, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::SMEM)); \
-    CGCN_CUDA(launch_k(fl::fused_layer_kernel<SV, MV, GV>, dim3(grid), dim3(fl::threads_for(GV)), fl::SMEM, stream, a)); \
+      CGCN_CUDA(cudaFuncSetAttribute(fl::fused_layer_kernel<SV, MV, GV, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::SMEM)); \
+    CGCN_CUDA(launch_k(fl::fused_layer_kernel<SV, MV, GV, PV>, dim3(grid), dim3(fl::threads_for(GV)), fl::SMEM, stream, a)); \
     return check_launch("fused_layer_kernel");                                                                      \
   }
+#define FL_CASE_G(SV, MV, GV) FL_CASE_P(SV, MV, GV, false) FL_CASE_P(SV, MV, GV, true)
 #define FL_CASE(SV, MV) FL_CASE_G(SV, MV, 16) FL_CASE_G(SV, MV, 8)
   FL_CASE(1, fl::FWD)
   FL_CASE(1, fl::FWD_STATS)
@@ -592,10 +603,26 @@ int fused_layer_launch(fl::Args a, int S, int mode, int* grid_out, cudaStream_t 
   FL_CASE(2, fl::FWD_STATS)
   FL_CASE(2, fl::BWD_MID)
   FL_CASE(2, fl::BWD_INPUT)
+#undef FL_CASE_P
 #undef FL_CASE_G
 #undef FL_CASE
   set_error("fused layer: unsupported strands=%d mode=%d", S, mode);
   return CGCN_ERR_INVALID;
+}
+
+int fused_layer_set_peer(fl::Args* a, const cgcn_peer_panel* pp, int n_local) {
+  CGCN_REQUIRE(pp != nullptr && pp->world >= 1 && pp->world <= CGCN_MAX_PEERS && pp->rank >= 0 && pp->rank < pp->world,
+               "fused layer: bad peer panel");
+  a->peer_world = pp->world;
+  for (int r = 0; r < pp->world; ++r) {
+    CGCN_REQUIRE(pp->base[r] != nullptr && pp->row_begin[r] <= pp->row_begin[r + 1], "fused layer: bad peer block %d", r);
+    a->peer_base[r] = pp->base[r];
+    a->peer_begin[r] = pp->row_begin[r];
+  }
+  a->peer_begin[pp->world] = pp->row_begin[pp->world];
+  CGCN_REQUIRE(pp->row_begin[pp->rank + 1] - pp->row_begin[pp->rank] == n_local, "fused layer: graph has %d rows, peer block %d",
+               n_local, pp->row_begin[pp->rank + 1] - pp->row_begin[pp->rank]);
+  return CGCN_OK;
 }
 
 }  // namespace cgcn

@@ -355,7 +355,7 @@ static const void* bwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.w
 // D^-1 dy, so that d W = ax^T dy is unchanged while the backward gather needs no per-neighbour scale.
 static bool use_fused(const cgcn_model* m) {
   static const bool off = getenv("CGCN_NO_FUSED") != nullptr;       // developer aid / A-B measurements
-  return !off && use_images(m) && fused_layer_supported(m->d, &m->graph) && m->peer == nullptr;
+  return !off && use_images(m) && fused_layer_supported(m->d, &m->graph);
 }
 
 static int prep_fwd_images(const Ctx& c) {
@@ -409,6 +409,7 @@ static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
     a.colidx = m->graph.colidx;
     a.n = c.n;
     a.gsrc = gather_src;
+    if (c.dist && m->peer != nullptr) CGCN_TRY(fused_layer_set_peer(&a, m->peer, c.n));      // neighbour rows over NVLink
     a.w = m->params.gc_w[l];
     a.w_transposed = 0;
     a.xin = xin;
@@ -581,6 +582,7 @@ static int bwd_propagate_fused(const Ctx& c, int l_from, const float* gather_src
   a.colidx = m->graph.colidx;
   a.n = c.n;
   a.gsrc = gather_src;
+  if (c.dist && m->peer != nullptr) CGCN_TRY(fused_layer_set_peer(&a, m->peer, c.n));
   a.w = m->params.gc_w[l_from];
   a.w_transposed = 1;
   a.dxd_in = ws + lay.dC;
