@@ -11,7 +11,7 @@ from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libchromegcn.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LAYERS = 4
 MAX_PEERS = 8
 
@@ -76,6 +76,10 @@ PROTOTYPES = {
     "cgcn_peer_close": (C.c_int, [_P]),
     "cgcn_peer_free": (C.c_int, [_P]),
     "cgcn_peer_publish": (C.c_int, [_P, _P, _SZ, _P]),
+    "cgcn_gcn_layer_fwd": (C.c_int, [C.POINTER(Graph), _I32, _P, _P, _P, _P, _P, _P, _I32, _F32, _U64, _U64, _I32, _P, _P, _P, _P,
+                                     _P, C.POINTER(_I32), _P]),
+    "cgcn_gcn_layer_bwd": (C.c_int, [C.POINTER(Graph), _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _F32, _U64, _U64, _I32, _P, _P, _P,
+                                     _P, C.POINTER(_I32), _P]),
     "cgcn_gemm_rowpanel": (C.c_int, [_P, _I64, _P, _I32, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _I32, _I32, _P, _SZ, _P]),
     "cgcn_gemm_gram_workspace_bytes": (_SZ, [_I64]),
     "cgcn_gemm_gram": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P, _SZ, _P]),
@@ -96,6 +100,7 @@ PROTOTYPES = {
     "cgcn_train_step_bits": (C.c_int, [C.POINTER(Model), _P, _P, _P, _P]),
     "cgcn_sgd_step": (C.c_int, [_P, _P, _P, _I64, _F32, _F32, _F32, _F32, _P]),
     "cgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _I64, _F32, _P]),
+    "cgcn_membw_read": (C.c_int, [_P, _SZ, _I32, _P, _P]),
     "cgcn_interleave_strands": (C.c_int, [C.POINTER(_P), _I32, _I32, _I32, _P, _P]),
     "cgcn_deinterleave_strands": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_P), _P]),
     "cgcn_dropout_mask": (C.c_int, [_P, _I32, _I32, _I32, _F32, _U64, _U64, _I32, _P]),

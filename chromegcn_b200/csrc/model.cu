@@ -810,6 +810,79 @@ extern "C" int cgcn_model_phase(const cgcn_model* m, int32_t kind, int32_t layer
 }
 extern "C" int cgcn_model_backward(const cgcn_model* m) { return model_backward(m); }
 
+extern "C" int cgcn_gcn_layer_fwd(const cgcn_graph* g, int32_t strands, const float* x_gather, const float* x_in,
+                                  const float* W, const float* b, const float* wg, const float* bg, int32_t gate_off,
+                                  float dropout_p, uint64_t seed, uint64_t step, int32_t site, float* sx, float* z,
+                                  float* x_out, float* gate, float* stats_partial, int32_t* parts_host, cgcn_stream_t stream) {
+  CGCN_REQUIRE(g && x_gather && x_in && W && b && sx && z && x_out && gate, "cgcn_gcn_layer_fwd: null argument");
+  CGCN_REQUIRE(gate_off || (wg && bg), "cgcn_gcn_layer_fwd: null gate parameters");
+  CGCN_REQUIRE(fused_layer_supported(128, g), "cgcn_gcn_layer_fwd: pattern graphs only (no value array)");
+  CGCN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "cgcn_gcn_layer_fwd: dropout_p=%f", dropout_p);
+  fl::Args a{};
+  a.rowptr = g->rowptr;
+  a.colidx = g->colidx;
+  a.n = g->n;
+  a.gsrc = x_gather;
+  a.w = W;
+  a.w_transposed = 0;
+  a.xin = x_in;
+  a.bias = b;
+  a.wg = wg;
+  a.bg = bg;
+  a.sx = sx;
+  a.z = z;
+  a.xo = x_out;
+  a.g = gate;
+  a.partial = stats_partial;
+  a.gate_off = gate_off;
+  a.drop = make_dropout(dropout_p, seed, step, site, dropout_p > 0.f, 0);
+  int parts = 0;
+  pdl_plain_next(static_cast<cudaStream_t>(stream));
+  CGCN_TRY(fused_layer_launch(a, strands, stats_partial ? fl::FWD_STATS : fl::FWD, &parts, static_cast<cudaStream_t>(stream)));
+  if (parts_host) *parts_host = parts;
+  return CGCN_OK;
+}
+
+extern "C" int cgcn_gcn_layer_bwd(const cgcn_graph* g, int32_t strands, const float* dys_gather, const float* dxd, const float* W,
+                                  const float* z_prev, const float* x_prev, const float* g_prev, const float* wg_prev,
+                                  int32_t gate_off, float dropout_p, uint64_t seed, uint64_t step, int32_t site_prev,
+                                  float* dys_out, float* dxd_out, float* dx_out, float* partial, int32_t* parts_host,
+                                  cgcn_stream_t stream) {
+  CGCN_REQUIRE(g && dys_gather && dxd && W, "cgcn_gcn_layer_bwd: null argument");
+  CGCN_REQUIRE(fused_layer_supported(128, g), "cgcn_gcn_layer_bwd: pattern graphs only (no value array)");
+  fl::Args a{};
+  a.rowptr = g->rowptr;
+  a.colidx = g->colidx;
+  a.n = g->n;
+  a.gsrc = dys_gather;
+  a.w = W;
+  a.w_transposed = 1;
+  a.dxd_in = dxd;
+  a.gate_off = gate_off;
+  int parts = 0;
+  pdl_plain_next(static_cast<cudaStream_t>(stream));
+  if (z_prev == nullptr) {
+    CGCN_REQUIRE(dx_out != nullptr, "cgcn_gcn_layer_bwd: null dx_out");
+    a.dx_out = dx_out;
+    a.drop = make_dropout(0.f, 0, 0, 0, false, 0);
+    CGCN_TRY(fused_layer_launch(a, strands, fl::BWD_INPUT, &parts, static_cast<cudaStream_t>(stream)));
+  } else {
+    CGCN_REQUIRE(x_prev && g_prev && (gate_off || wg_prev) && dys_out && partial, "cgcn_gcn_layer_bwd: null layer-below argument");
+    CGCN_REQUIRE(dys_out != dys_gather, "cgcn_gcn_layer_bwd: dys_out must not alias the gathered panel");
+    a.wg = wg_prev;
+    a.z_prev = z_prev;
+    a.x_prev = x_prev;
+    a.g_prev = g_prev;
+    a.dys_out = dys_out;
+    a.dxd_out = dxd_out;
+    a.partial = partial;
+    a.drop = make_dropout(dropout_p, seed, step, site_prev, dropout_p > 0.f, 0);
+    CGCN_TRY(fused_layer_launch(a, strands, fl::BWD_MID, &parts, static_cast<cudaStream_t>(stream)));
+  }
+  if (parts_host) *parts_host = parts;
+  return CGCN_OK;
+}
+
 static int train_step(const cgcn_model* m, const float* target, const uint32_t* target_bits, float* probs, float* loss_sum_out,
                       float* out_grad_scratch) {
   CGCN_REQUIRE(m && (target || target_bits) && loss_sum_out && out_grad_scratch, "cgcn_train_step: null argument");

@@ -691,6 +691,37 @@ __global__ void dropout_mask_kernel(float4* mask, int64_t total4, DropoutCfg cfg
     mask[i] = cfg.enabled ? dropout_mult4(cfg, static_cast<uint64_t>(i)) : make_float4(1.f, 1.f, 1.f, 1.f);
 }
 
+// Read-bandwidth probe (tools/l2_bw.py): every CTA streams the whole buffer `reps` times with 8 independent 128-bit
+// loads in flight per thread.  A buffer that fits L2 (<= 64 MB) measures the L2 -> SM read rate the gather kernels
+// can hope for; a buffer of several GB measures the HBM read rate.
+__global__ void __launch_bounds__(256) membw_read_kernel(const float4* __restrict__ p, size_t n4, int reps, float* sink) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (int r = 0; r < reps; ++r) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < n4; i += 8 * stride) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + i + u * stride);      // L2 only: a hit in L1 would not be an L2 read
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x += v[u].x;
+        acc.y += v[u].y;
+        acc.z += v[u].z;
+        acc.w += v[u].w;
+      }
+    }
+    for (; i < n4; i += stride) {
+      const float4 v = __ldcg(p + i);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 1.2345e-30f) *sink = acc.x;      // keeps the loads alive
+}
+
 // =============================================================================== host launchers
 static int flat_grid(int64_t work_items, int threads) {
   int64_t b = (work_items + threads - 1) / threads;
@@ -912,6 +943,13 @@ extern "C" int cgcn_adam_step(float* params, const float* grads, float* exp_avg,
       params, grads, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, static_cast<float>(bc1),
       static_cast<float>(sqrt(bc2)), grad_scale);
   return check_launch("adam_kernel");
+}
+
+extern "C" int cgcn_membw_read(const float* buf, size_t bytes, int32_t reps, float* sink, cgcn_stream_t stream) {
+  CGCN_REQUIRE(buf && sink && bytes >= 16 && reps >= 1, "cgcn_membw_read: bad argument");
+  membw_read_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(buf), bytes / 16,
+                                                                                reps, sink);
+  return check_launch("membw_read_kernel");
 }
 
 extern "C" int cgcn_interleave_strands(const float* const* src_host, int32_t strands, int32_t n, int32_t d, float* dst,

@@ -80,6 +80,33 @@ def spmm_peer(graph: HiCGraph, blocks: Sequence[torch.Tensor], rank: int, mean: 
     return out
 
 
+def gcn_layer_fwd(graph: HiCGraph, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, gate_w: Optional[torch.Tensor],
+                  gate_b: Optional[torch.Tensor], gate_off: bool = False, dropout_p: float = 0.0, seed: int = 0, step: int = 0,
+                  site: int = 0, with_stats: bool = False, x_gather: Optional[torch.Tensor] = None):
+    """One gated GCN layer (models/ChromeModels.py:37-40) as one fused kernel (cgcn_gcn_layer_fwd).  `x` is
+    `[n, 128]` or the strand-interleaved `[n, S, 128]`.  Returns `(x_out, z, gate, sx, stats)`; `stats` is the
+    `[parts, 2*S*128]` per-CTA column sums of relu(x_out), relu(x_out)^2 (None unless `with_stats`)."""
+    lib = _lib.load()
+    x = _f32c(x)
+    n = graph.n
+    S = x.shape[1] if x.dim() == 3 else 1
+    dev = x.device
+    xg = x if x_gather is None else _f32c(x_gather)
+    sx, z, xo = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    gate = torch.empty(n, S, dtype=torch.float32, device=dev)
+    stats = torch.zeros(512, 2 * S * 128, dtype=torch.float32, device=dev) if with_stats else None
+    parts = C.c_int32(0)
+    gs = graph.c_struct()
+    with torch.cuda.device(dev):
+        _lib.check(lib.cgcn_gcn_layer_fwd(C.byref(gs), S, xg.data_ptr(), x.data_ptr(), _f32c(weight).data_ptr(),
+                                          _f32c(bias).data_ptr(), _lib.ptr(None if gate_w is None else _f32c(gate_w)),
+                                          _lib.ptr(None if gate_b is None else _f32c(gate_b)), 1 if gate_off else 0,
+                                          float(dropout_p), seed, step, site, sx.data_ptr(), z.data_ptr(), xo.data_ptr(),
+                                          gate.data_ptr(), _lib.ptr(stats), C.byref(parts), _lib.current_stream()),
+                   "cgcn_gcn_layer_fwd")
+    return xo, z, gate, sx, (stats[: parts.value] if with_stats else None)
+
+
 def gemm_rowpanel(a: torch.Tensor, b: torch.Tensor, b_transposed: bool = False, bias: Optional[torch.Tensor] = None,
                   rowscale_graph: Optional[HiCGraph] = None, rowscale_group: int = 1, impl: int = GEMM_AUTO,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CGCN_ABI_VERSION 6
+#define CGCN_ABI_VERSION 7
 #define CGCN_MAX_LAYERS 4
 #define CGCN_MAX_PEERS 8    /* GPUs of one NVSwitch box */
 
@@ -186,6 +186,42 @@ typedef struct cgcn_peer_panel {
  * column indices; out / residual are local [g->n][width]. */
 int cgcn_spmm_peer(const cgcn_graph* g, const cgcn_peer_panel* panel, float* out, int32_t width, int32_t scale_mode,
                    const float* residual, cgcn_stream_t stream);
+
+/* ------------------------------- piece 2c: one gated GCN layer as ONE kernel (d = 128) ---- */
+/*
+ * The layer of models/ChromeModels.py:37-40 (and its repeat :42-46) around GraphConvolution.forward
+ * (models/SubLayers.py:42-52) for `strands` interleaved feature sets, as one persistent sm_100a kernel
+ * (csrc/fused_layer.cu): CSR gather-reduce -> tcgen05 3xTF32 contraction with the weights stationary in tensor
+ * memory -> epilogue.
+ *   sx  = P x_gather                (un-normalised neighbour sums, saved: d W = sx^T (D^-1 dy))
+ *   y   = (D^-1 sx) W + b ; z = tanh(y) ; g = sigmoid(z . wg + bg)   (g == 1 when gate_off)
+ *   x_out = dropout((1-g) x_in + g z)   (keep-mask of cgcn_dropout_mask(seed, step, site); dropout_p == 0: none)
+ * x_gather is the panel the column indices address ([*][strands][128]; x_in itself on one GPU, the all-gathered
+ * copy for a row-partitioned graph); x_in / sx / z / x_out are the local rows [g->n][strands][128]; gate is
+ * [g->n][strands].  stats_partial (may be NULL): [*parts_host][2*strands*128] per-CTA column sums of relu(x_out) and
+ * relu(x_out)^2 (BatchNorm statistics of the head), *parts_host <= the device's SM count.
+ * Pattern graphs only (g->vals == NULL); W is [128 in][128 out] row major.
+ */
+int cgcn_gcn_layer_fwd(const cgcn_graph* g, int32_t strands, const float* x_gather, const float* x_in,
+                       const float* W, const float* b, const float* wg, const float* bg, int32_t gate_off,
+                       float dropout_p, uint64_t seed, uint64_t step, int32_t site,
+                       float* sx, float* z, float* x_out, float* gate,
+                       float* stats_partial, int32_t* parts_host, cgcn_stream_t stream);
+/*
+ * Its autograd twin for the gradient entering the layer below:  with t = D^-1 dy of THIS layer (dys, gathered through
+ * the symmetric pattern) and dxd = (1-g) dh of this layer,
+ *   dx = (P dys) W^T + dxd                                         (A_hat^T G W^T re-associated so the gather comes first)
+ * and, when z_prev != NULL, the gate / tanh backward of the layer below on dx in the same kernel:
+ *   dh = dx * mask(site_prev) ; dgp = (sum_c dh (z_prev - x_prev)) g_prev (1 - g_prev) ;
+ *   dz = g_prev dh + dgp wg_prev ; dy_prev = dz (1 - z_prev^2) ; dys_out = D^-1 dy_prev ; dxd_out = (1 - g_prev) dh
+ *   partial[*parts_host][2*128+4]: per-CTA column sums of dy_prev | dgp z_prev | dgp   (d b, d w_g, d b_g)
+ * With z_prev == NULL, dx is written to dx_out (d loss / d x_in) and nothing else.  dxd_out may be NULL or alias dxd.
+ */
+int cgcn_gcn_layer_bwd(const cgcn_graph* g, int32_t strands, const float* dys_gather, const float* dxd, const float* W,
+                       const float* z_prev, const float* x_prev, const float* g_prev, const float* wg_prev, int32_t gate_off,
+                       float dropout_p, uint64_t seed, uint64_t step, int32_t site_prev,
+                       float* dys_out, float* dxd_out, float* dx_out, float* partial, int32_t* parts_host,
+                       cgcn_stream_t stream);
 
 /* ------------------------------------------------ piece 3: dense contractions ---- */
 /* gemm_impl: 0 = auto (tcgen05 when the shape allows), 1 = fp32 FFMA kernel, 2 = tcgen05 3xTF32. */
@@ -355,6 +391,9 @@ int cgcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                    cgcn_stream_t stream);
 
 /* --------------------------------------------------------------- utilities ---- */
+/* Read-bandwidth probe (measurement aid, tools/l2_bw.py): streams `bytes` of `buf` `reps` times with L2-only loads.  A
+ * buffer that fits L2 gives the L2 -> SM read rate, one of several GB the HBM read rate.  sink: one float. */
+int cgcn_membw_read(const float* buf, size_t bytes, int32_t reps, float* sink, cgcn_stream_t stream);
 /* [n][d] x strands  <->  [n][strands][d].  src/dst arrays of `strands` pointers are HOST arrays. */
 int cgcn_interleave_strands(const float* const* src_host, int32_t strands, int32_t n, int32_t d, float* dst,
                             cgcn_stream_t stream);

@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_abi_version_and_struct_layout(lib):
     import ctypes as C
     from chromegcn_b200 import _lib
-    assert lib.cgcn_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.cgcn_abi_version() == _lib.ABI_VERSION == 7
     assert lib.cgcn_sizeof(0) == C.sizeof(_lib.Graph)
     assert lib.cgcn_sizeof(1) == C.sizeof(_lib.Params)
     assert lib.cgcn_sizeof(2) == C.sizeof(_lib.Model)
