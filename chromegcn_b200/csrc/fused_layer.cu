@@ -108,7 +108,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
 }
 
-template <int S, int MODE, int G_WARPS, bool PEER>
+template <int S, int MODE, int G_WARPS, bool PEER, int SRC>
 __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -181,8 +181,122 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
     // while batch i is being summed, batch i+1 -- of the same segment, or the first of the next row / tile -- is already
     // in flight, so the load queue never drains at a row or tile boundary.  Column indices are fetched two segments
     // ahead, row pointers two tiles ahead.  Sums run in CSR order (deterministic).
-    constexpr int U = (G_WARPS == 8) ? ((S == 2) ? 8 : 12) : ((S == 2) ? 3 : 6);
     const int gw = warp - EPI_WARPS;
+    // ---- MMA issue (first gather warp, after it has delivered its own rows of the tile)
+    constexpr uint32_t idesc = idesc_m128_n64();
+    auto issue_mma = [&](int t) {
+      const uint32_t accb = t & 1;
+      if (t == 0) {                                // the weight images are in tensor memory (see above)
+        named_bar_sync(3, (EPI_WARPS + 1) * 32);
+        tc_fence_after();
+      }
+      mbar_wait(bar_tempty + 8 * accb, ((t >> 1) & 1) ^ 1);
+      mbar_wait(bar_a_full, t & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + TM_ACC + accb * 64;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t k0 = kc * 32 + ks * 8;                 // TMEM column of this k-step inside a weight image
+            const uint64_t dxh = make_desc(sA + kc * A_CHUNK + ks * 32, 16, 1024);
+            const uint64_t dxl = make_desc(sA + 4 * A_CHUNK + kc * A_CHUNK + ks * 32, 16, 1024);
+            umma_tf32_ts(d_tmem, tmem_base + TM_WLO + k0, dxh, idesc, (kc | ks) != 0);      // small terms first
+            umma_tf32_ts(d_tmem, tmem_base + TM_WHI + k0, dxl, idesc, 1);
+            umma_tf32_ts(d_tmem, tmem_base + TM_WHI + k0, dxh, idesc, 1);
+          }
+        }
+        umma_commit(bar_a_empty);                  // tile buffer free once these MMAs retire
+        umma_commit(bar_tfull + 8 * accb);         // accumulator complete
+      }
+      __syncwarp();
+    };
+
+
+    // one finished panel row (lane owns columns 4 lane .. 4 lane + 3) into the tile buffer as hi / lo TF32
+    auto put_row = [&](int pr, const float4 v) {
+      uint4 hi, lo;
+      split4(v, hi, lo);
+      const uint32_t off = (lane >> 3) * A_CHUNK + (pr >> 3) * 1024 + (pr & 7) * 128 + (((lane & 7) ^ (pr & 7)) << 4);
+      sts128(sA + off, hi);
+      sts128(sA + 4 * A_CHUNK + off, lo);
+    };
+    auto deliver = [&](int t) {                    // this warp's rows of tile t are in the buffer
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full);
+      if (warp == ISSUE_WARP) issue_mma(t);
+    };
+
+    if constexpr (SRC != GATHER) {
+      // ---- streaming producer: the tile is rows of gsrc (already aggregated by the SpMM, or the head's input), NT tiles
+      // of look-ahead in a register ring: 12 coalesced 512-byte loads in flight per warp, continuously
+      constexpr int NT = 3, RP = RPW * S;
+      float4 ring[NT][RP];
+      int ring_deg[NT][RPW];
+      auto load_tile = [&](int t, float4 (&b)[RP], int (&dg)[RPW]) {
+#pragma unroll
+        for (int h = 0; h < RPW; ++h) {
+          const int row = r_begin + t * TG + gw + G_WARPS * h;
+          const bool valid = t < ntile && row < r_end;
+          dg[h] = 1;
+          if (FORWARD && SRC == STREAM && valid) dg[h] = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            b[h * S + s] = valid ? ldg4(a.gsrc + (static_cast<size_t>(row) * S + s) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 bn_m[S], bn_r[S], bn_g = make_float4(0.f, 0.f, 0.f, 0.f), bn_b = bn_g;
+      if constexpr (SRC == STREAM_BN) {
+        bn_g = ldg4(a.bn_gamma + lane * 4);
+        bn_b = ldg4(a.bn_beta + lane * 4);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          bn_m[s] = ldg4(a.bn_mean + s * 128 + lane * 4);
+          bn_r[s] = ldg4(a.bn_rstd + s * 128 + lane * 4);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) load_tile(j, ring[j], ring_deg[j]);
+#pragma unroll 1
+      for (int t0 = 0; t0 < ntile; t0 += NT) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int t = t0 + j;
+          if (t < ntile) {
+            mbar_wait(bar_a_empty, (t & 1) ^ 1);
+#pragma unroll
+            for (int h = 0; h < RPW; ++h) {
+              const int lr = gw + G_WARPS * h;
+              const int row = r_begin + t * TG + lr;
+              float scale = 1.0f;
+              if (FORWARD && SRC == STREAM) scale = ring_deg[j][h] > 0 ? __fdiv_rn(1.0f, static_cast<float>(ring_deg[j][h])) : 1.0f;
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                float4 v = ring[j][h * S + s];
+                if constexpr (SRC == STREAM_BN) {
+                  v = make_float4((fmaxf(v.x, 0.f) - bn_m[s].x) * bn_r[s].x * bn_g.x + bn_b.x, (fmaxf(v.y, 0.f) - bn_m[s].y) * bn_r[s].y * bn_g.y + bn_b.y,
+                                  (fmaxf(v.z, 0.f) - bn_m[s].z) * bn_r[s].z * bn_g.z + bn_b.z, (fmaxf(v.w, 0.f) - bn_m[s].w) * bn_r[s].w * bn_g.w + bn_b.w);
+                  const size_t ofs = (static_cast<size_t>(row) * S + s) * 128 + lane * 4;
+                  if (a.drop.enabled) {
+                    const float4 m = dropout_mult4(a.drop, ofs >> 2);
+                    v = make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w);
+                  }
+                  if (row < r_end) st4(a.hb_out + ofs, v);
+                } else {
+                  v = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+                }
+                put_row(lr * S + s, v);
+              }
+            }
+            deliver(t);
+            load_tile(t + NT, ring[j], ring_deg[j]);
+          }
+        }
+      }
+    } else {
+    constexpr int U = (G_WARPS == 8) ? ((S == 2) ? 8 : 12) : ((S == 2) ? 3 : 6);
     const int nrow = ntile * RPW;                  // rows this warp visits; rows beyond r_end read as empty
     auto load_ptrs = [&](int t) -> int {           // lane 2h + e holds rowptr[row_h + e] of tile t
       int v = 0;
@@ -244,37 +358,6 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
         }
       }
     };
-    // ---- MMA issue (first gather warp, after it has delivered its own rows of the tile)
-    constexpr uint32_t idesc = idesc_m128_n64();
-    auto issue_mma = [&](int t) {
-      const uint32_t accb = t & 1;
-      if (t == 0) {                                // the weight images are in tensor memory (see above)
-        named_bar_sync(3, (EPI_WARPS + 1) * 32);
-        tc_fence_after();
-      }
-      mbar_wait(bar_tempty + 8 * accb, ((t >> 1) & 1) ^ 1);
-      mbar_wait(bar_a_full, t & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t d_tmem = tmem_base + TM_ACC + accb * 64;
-#pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t k0 = kc * 32 + ks * 8;                 // TMEM column of this k-step inside a weight image
-            const uint64_t dxh = make_desc(sA + kc * A_CHUNK + ks * 32, 16, 1024);
-            const uint64_t dxl = make_desc(sA + 4 * A_CHUNK + kc * A_CHUNK + ks * 32, 16, 1024);
-            umma_tf32_ts(d_tmem, tmem_base + TM_WLO + k0, dxh, idesc, (kc | ks) != 0);      // small terms first
-            umma_tf32_ts(d_tmem, tmem_base + TM_WHI + k0, dxl, idesc, 1);
-            umma_tf32_ts(d_tmem, tmem_base + TM_WHI + k0, dxh, idesc, 1);
-          }
-        }
-        umma_commit(bar_a_empty);                  // tile buffer free once these MMAs retire
-        umma_commit(bar_tfull + 8 * accb);         // accumulator complete
-      }
-      __syncwarp();
-    };
-
     float4 X[U][S], Y[U][S];
     int c_cols, c_cl, n_cols, n_cl, nn_cols, nn_cl;        // current / next / next-next segment
     next_seg(c_cols, c_cl);
@@ -341,6 +424,7 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
       n_cl = nn_cl;
       next_seg(nn_cols, nn_cl);
     }
+    }
   } else {
     // =========================================================== epilogue warps
     // Phase A (thread = output feature: the accumulator is y^T, TMEM lane f = feature f, column r = tile row r):
@@ -353,7 +437,9 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
 #pragma unroll
     for (int i = 0; i < NST; ++i) st0[i] = st1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float bg = (FORWARD && !a.gate_off) ? __ldg(a.bg) : 0.f;
-    const float bias_f = FORWARD ? __ldg(a.bias + threadIdx.x) : 0.f;      // threadIdx.x = this thread's feature
+    float bias_f = 0.f;                            // threadIdx.x = this thread's feature
+    if (FORWARD) bias_f = __ldg(a.bias + threadIdx.x);
+    if (MODE == HEAD_FWD && static_cast<int>(threadIdx.x) < a.w_rows) bias_f = __ldg(a.bias + threadIdx.x);
     const int64_t prow_end = static_cast<int64_t>(r_end) * S;
 
     for (int t = 0; t < ntile; ++t) {
@@ -390,7 +476,7 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
             for (int cc = 0; cc < 4; ++cc) {
               if constexpr (FORWARD) {
                 prefetch_l1(a.xin + nofs + cc * 32);
-              } else {
+              } else if constexpr (MODE != HEAD_FWD) {
                 prefetch_l1(a.dxd_in + nofs + cc * 32);
                 if constexpr (MODE == BWD_MID) {
                   prefetch_l1(a.z_prev + nofs + cc * 32);
@@ -438,6 +524,12 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
                 st1[cc].x += rl.x * rl.x; st1[cc].y += rl.y * rl.y; st1[cc].z += rl.z * rl.z; st1[cc].w += rl.w * rl.w;
               }
             }
+          }
+        } else if constexpr (MODE == HEAD_FWD) {     // logits: the first out_ld columns of the row (bias added in phase A)
+          if (valid) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (cc * 32 + 4 * q < a.out_ld) st4(a.out + static_cast<size_t>(grow) * a.out_ld + cc * 32 + 4 * q, y[cc]);
           }
         } else if constexpr (MODE == BWD_INPUT) {
           if (valid) {
@@ -575,7 +667,8 @@ int fused_layer_grid(int n, int S, int* rows_per_cta_out) {
 bool fused_layer_supported(int d, const cgcn_graph* g) { return d == 128 && g != nullptr && g->vals == nullptr; }
 
 int fused_layer_launch(fl::Args a, int S, int mode, int* grid_out, cudaStream_t stream) {
-  CGCN_REQUIRE(a.rowptr && a.colidx && (a.gsrc || a.peer_world > 0) && a.w, "fused layer: null graph / panel / weight");
+  CGCN_REQUIRE((a.source != fl::GATHER || (a.rowptr && a.colidx)) && (a.gsrc || a.peer_world > 0) && a.w,
+               "fused layer: null graph / panel / weight");
   CGCN_REQUIRE(S == 1 || S == 2, "fused layer: strands=%d", S);
   int rows = 0;
   const int grid = fused_layer_grid(a.n, S, &rows);
@@ -585,27 +678,28 @@ int fused_layer_launch(fl::Args a, int S, int mode, int* grid_out, cudaStream_t 
   static const int gw = (getenv("CGCN_FUSED_GW") != nullptr && atoi(getenv("CGCN_FUSED_GW")) == 8) ? 8 : 16;
   const bool peer = a.peer_world > 0;
   if (peer) a.gsrc = a.peer_base[0];
-#define FL_CASE_P(SV, MV, GV, PV)                                                                                    \
-  if (S == SV && mode == MV && gw == GV && peer == PV) {                                                             \
+  const int src = a.source;
+  CGCN_REQUIRE(!(peer && src != fl::GATHER), "fused layer: peer panels are gathered, not streamed");
+  CGCN_REQUIRE((mode == fl::HEAD_FWD) == (src == fl::STREAM_BN), "fused layer: HEAD_FWD goes with STREAM_BN");
+#define FL_LAUNCH(SV, MV, GV, PV, RV)                                                                                \
+  if (S == SV && mode == MV && gwsel == GV && peer == PV && src == RV) {                                             \
     static bool attr_set[64] = {};                                                                                   \
     if (first_use_on_device(attr_set))                                                                               \
-      CGCN_CUDA(cudaFuncSetAttribute(fl::fused_layer_kernel<SV, MV, GV, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::SMEM)); \
-    CGCN_CUDA(launch_k(fl::fused_layer_kernel<SV, MV, GV, PV>, dim3(grid), dim3(fl::threads_for(GV)), fl::SMEM, stream, a)); \
+      CGCN_CUDA(cudaFuncSetAttribute(fl::fused_layer_kernel<SV, MV, GV, PV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::SMEM)); \
+    CGCN_CUDA(launch_k(fl::fused_layer_kernel<SV, MV, GV, PV, RV>, dim3(grid), dim3(fl::threads_for(GV)), fl::SMEM, stream, a)); \
     return check_launch("fused_layer_kernel");                                                                      \
   }
-#define FL_CASE_G(SV, MV, GV) FL_CASE_P(SV, MV, GV, false) FL_CASE_P(SV, MV, GV, true)
-#define FL_CASE(SV, MV) FL_CASE_G(SV, MV, 16) FL_CASE_G(SV, MV, 8)
-  FL_CASE(1, fl::FWD)
-  FL_CASE(1, fl::FWD_STATS)
-  FL_CASE(1, fl::BWD_MID)
-  FL_CASE(1, fl::BWD_INPUT)
-  FL_CASE(2, fl::FWD)
-  FL_CASE(2, fl::FWD_STATS)
-  FL_CASE(2, fl::BWD_MID)
-  FL_CASE(2, fl::BWD_INPUT)
-#undef FL_CASE_P
-#undef FL_CASE_G
-#undef FL_CASE
+  const int gwsel = (src == fl::GATHER) ? gw : 16;
+#define FL_MODES(SV, GV, PV, RV) \
+  FL_LAUNCH(SV, fl::FWD, GV, PV, RV) FL_LAUNCH(SV, fl::FWD_STATS, GV, PV, RV) FL_LAUNCH(SV, fl::BWD_MID, GV, PV, RV) FL_LAUNCH(SV, fl::BWD_INPUT, GV, PV, RV)
+#define FL_STRANDS(SV)                                                                                   \
+  FL_MODES(SV, 16, false, fl::GATHER) FL_MODES(SV, 16, true, fl::GATHER) FL_MODES(SV, 8, false, fl::GATHER) \
+  FL_MODES(SV, 16, false, fl::STREAM) FL_LAUNCH(SV, fl::HEAD_FWD, 16, false, fl::STREAM_BN)
+  FL_STRANDS(1)
+  FL_STRANDS(2)
+#undef FL_LAUNCH
+#undef FL_MODES
+#undef FL_STRANDS
   set_error("fused layer: unsupported strands=%d mode=%d", S, mode);
   return CGCN_ERR_INVALID;
 }

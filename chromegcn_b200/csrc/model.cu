@@ -353,10 +353,26 @@ static const void* bwd_image(const Ctx& c, int i) { return use_images(c.m) ? c.w
 // The fused layer kernels (fused_layer.cu): one launch per layer and direction instead of SpMM + contraction + gate
 // kernel.  In this mode the saved `ax` panels hold the UN-normalised neighbour sums and the `dy` panels hold
 // D^-1 dy, so that d W = ax^T dy is unchanged while the backward gather needs no per-neighbour scale.
-static bool use_fused(const cgcn_model* m) {
+// Layer modes: 0 = three kernels per layer (SpMM, row-panel contraction, gate kernel); 1 = "gather" (default for Hi-C
+// degrees): everything in one kernel, CSR gather included; 2 = "stream": the standalone SpMM + ONE kernel for contraction,
+// gate, blend, dropout and column partials, its operand tile streamed from the SpMM's output.  Modes 1 and 2 share the
+// conventions above.  Measured on B200, whole genome (mean degree 10.7), ms per pass: unfused 16.9, gather 16.0 -> 15.7,
+// stream 18.2 (profiles/r02_layer_modes.md): the contraction + epilogue kernel is bound by its four epilogue warps
+// (one per scheduler), not by where its operand comes from.  The all-in-one kernel keeps ~200 gather loads in flight per
+// SM against the SpMM's ~320, so once the gather dominates (mean degree 51: fused 6.5 ms per layer vs SpMM 2.15 + 0.6 +
+// 0.9) mode 0 wins: graphs beyond CGCN_FUSED_MAX_DEGREE (default 24) stored entries per row use it.
+static int layer_mode(const cgcn_model* m) {
+  static const char* env = getenv("CGCN_LAYER_MODE");              // "unfused" | "gather" | "stream"
   static const bool off = getenv("CGCN_NO_FUSED") != nullptr;       // developer aid / A-B measurements
-  return !off && use_images(m) && fused_layer_supported(m->d, &m->graph);
+  if (off || !use_images(m) || !fused_layer_supported(m->d, &m->graph)) return 0;
+  if (env != nullptr && strcmp(env, "unfused") == 0) return 0;
+  if (env != nullptr && strcmp(env, "stream") == 0) return 2;
+  if (env != nullptr && strcmp(env, "gather") == 0) return 1;
+  static const int max_deg = getenv("CGCN_FUSED_MAX_DEGREE") ? atoi(getenv("CGCN_FUSED_MAX_DEGREE")) : 24;
+  const int64_t nnz = m->graph.nnz, n = m->graph.n > 0 ? m->graph.n : 1;
+  return nnz <= static_cast<int64_t>(max_deg) * n ? 1 : 0;
 }
+static bool use_fused(const cgcn_model* m) { return layer_mode(m) != 0; }
 
 static int prep_fwd_images(const Ctx& c) {
   pdl_plain_next(c.st);              // first kernel of a pass: ordinary stream order against whatever ran before
@@ -408,8 +424,18 @@ static int fwd_layer(const Ctx& c, int l, const float* gather_src) {
     a.rowptr = m->graph.rowptr;
     a.colidx = m->graph.colidx;
     a.n = c.n;
-    a.gsrc = gather_src;
-    if (c.dist && m->peer != nullptr) CGCN_TRY(fused_layer_set_peer(&a, m->peer, c.n));      // neighbour rows over NVLink
+    if (layer_mode(m) == 2) {
+      // sx = P x by the SpMM kernel (un-normalised sums), then the contraction + epilogue kernel streams it
+      if (c.dist && m->peer != nullptr)
+        CGCN_TRY(spmm_peer_launch(&m->graph, m->peer, ws + lay.ax[l], c.W, 0, nullptr, c.st));
+      else
+        CGCN_TRY(spmm_launch(&m->graph, gather_src, ws + lay.ax[l], c.W, 0, nullptr, c.st));
+      a.source = fl::STREAM;
+      a.gsrc = ws + lay.ax[l];
+    } else {
+      a.gsrc = gather_src;
+      if (c.dist && m->peer != nullptr) CGCN_TRY(fused_layer_set_peer(&a, m->peer, c.n));      // neighbour rows over NVLink
+    }
     a.w = m->params.gc_w[l];
     a.w_transposed = 0;
     a.xin = xin;
@@ -460,6 +486,28 @@ static int fwd_head(const Ctx& c) {
     CGCN_TRY(bn_finalize_launch(ws + lay.partial, 0, c.n_total, c.S, c.d, m->bn_eps, m->bn_momentum, m->training,
                                 m->bn_running_mean, m->bn_running_var, m->bn_num_batches_tracked, ws + lay.bn_mean,
                                 ws + lay.bn_rstd, m->training ? m->bn_sums : nullptr, nullptr, c.st));
+  const int ldo_f = m->out_ld > 0 ? m->out_ld : c.C;
+  static const bool fused_head = getenv("CGCN_FUSED_HEAD") != nullptr;      // measured 62.6 us vs 27 + 29 for the two kernels below
+  if (fused_head && use_fused(m) && ldo_f % 4 == 0) {
+    // hb = dropout(BatchNorm(relu(x))) in the producer warps, out = hb Wout^T + bout on the tensor cores: one kernel
+    fl::Args a{};
+    a.n = c.n;
+    a.source = fl::STREAM_BN;
+    a.gsrc = ws + lay.xo[c.L - 1];
+    a.bn_mean = ws + lay.bn_mean;
+    a.bn_rstd = ws + lay.bn_rstd;
+    a.bn_gamma = m->params.bn_w;
+    a.bn_beta = m->params.bn_b;
+    a.hb_out = ws + lay.hb;
+    a.drop = make_dropout(m->dropout_p, m->seed, m->step, 1, m->training, c.drop_off);
+    a.w = m->params.out_w;
+    a.w_transposed = 1;
+    a.w_rows = c.C;
+    a.bias = m->params.out_b;
+    a.out = m->out;
+    a.out_ld = ldo_f;
+    return fused_layer_launch(a, c.S, fl::HEAD_FWD, nullptr, c.st);
+  }
   // hb = dropout(BatchNorm(relu(x)))                 (models/ChromeModels.py:48-50)
   BnApplyArgs b{};
   b.h = ws + lay.xo[c.L - 1];
@@ -581,8 +629,19 @@ static int bwd_propagate_fused(const Ctx& c, int l_from, const float* gather_src
   a.rowptr = m->graph.rowptr;
   a.colidx = m->graph.colidx;
   a.n = c.n;
-  a.gsrc = gather_src;
-  if (c.dist && m->peer != nullptr) CGCN_TRY(fused_layer_set_peer(&a, m->peer, c.n));
+  if (layer_mode(m) == 2) {
+    // u = P dys by the SpMM kernel into a scratch panel (dX: the head's d hb, dead since its gate stage)
+    float* u = ws + lay.dX;
+    if (c.dist && m->peer != nullptr)
+      CGCN_TRY(spmm_peer_launch(&m->graph, m->peer, u, c.W, 0, nullptr, c.st));
+    else
+      CGCN_TRY(spmm_launch(&m->graph, gather_src, u, c.W, 0, nullptr, c.st));
+    a.source = fl::STREAM;
+    a.gsrc = u;
+  } else {
+    a.gsrc = gather_src;
+    if (c.dist && m->peer != nullptr) CGCN_TRY(fused_layer_set_peer(&a, m->peer, c.n));
+  }
   a.w = m->params.gc_w[l_from];
   a.w_transposed = 1;
   a.dxd_in = ws + lay.dC;

@@ -16,6 +16,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from oracle import adjacency as oadj
 from oracle import gcn as ogcn
 
 pytestmark = pytest.mark.gpu
@@ -558,3 +559,96 @@ def test_sharded_epoch_round_is_one_step_on_the_mean_gradient():
     assert ogcn.max_rel(losses.cpu(), torch.tensor(want_losses)) <= FWD_TOL
     for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
         assert ogcn.max_rel(p.detach().cpu(), q.detach()) <= 2e-5, k
+
+
+def test_module_api_training_loop_with_flat_optimizer_matches_oracle():
+    """The reference's own loop -- optimizer.zero_grad(); forward x2 through the module API; loss.backward();
+    optimizer.step() (finetune.py:39-49) -- for several steps with this package's ChromeGCN and get_optimizer().  After the
+    first step every p.grad is a view of the flat gradient buffer and autograd ACCUMULATES into it, so zero_grad() must
+    really clear it: the trajectory has to follow the oracle's, not the running sum of gradients."""
+    import argparse
+    from chromegcn_b200 import synthetic
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.graph import HiCGraph
+    from chromegcn_b200.optim import get_optimizer
+    h = synthetic.make_hic("chr21", hic_edges=4000, n_windows=500, n_bins=1400)
+    ip, ix = oadj.build_adjacency_numpy(h.window_starts, h.bin1, h.bin2, h.val, h.norm, 1, 4000)
+    n = ip.shape[0] - 1
+    f = synthetic.make_features("chr21", n, 128, 9)
+    for kind in ("sgd", "adam"):
+        torch.manual_seed(11)
+        om = ogcn.stress_init_(ogcn.ChromeGCNOracle(128, 128, 9, 0.0, True, 2))
+        m = ChromeGCN(128, 128, 9, 0.0, True, 2)
+        m.load_state_dict(om.state_dict())
+        m = m.to(_dev()).train()
+        lr = 0.05 if kind == "sgd" else 1e-3
+        opt = get_optimizer(m, argparse.Namespace(optim=kind, lr=lr))
+        oopt = ogcn.make_optimizer(om, kind, lr)
+        g = HiCGraph.from_csr_pattern(ip, ix, _dev())
+        adj = ogcn.coo_adjacency(ip, ix)
+        xf, xr, tg = f["forward"].to(_dev()), f["backward"].to(_dev()), f["target"].to(_dev())
+        for step in range(4):
+            opt.zero_grad()
+            _, pf, _, _ = m(xf, g, None)
+            _, pr, _, _ = m(xr, g, None)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits((pf + pr) / 2, tg)
+            loss.backward()
+            opt.step()
+            lo, _, _, _ = ogcn.chromosome_step(om, f["forward"], f["backward"], f["target"], adj, oopt, True)
+            assert abs(loss.item() - lo) <= 2e-5 * abs(lo), (kind, step, loss.item(), lo)
+        for k, v in om.state_dict().items():
+            if "num_batches" in k:
+                continue
+            assert ogcn.max_rel(m.state_dict()[k].cpu(), v) <= 1e-4, (kind, k)
+
+
+def test_three_epoch_trajectory_on_a_chr22_sized_graph_keeps_per_label_auroc_aupr():
+    """on the DEFAULT path (fused layer kernels, tcgen05 3xTF32 contractions) a three-epoch
+    finetune() trajectory on a C1-sized graph (N = 20 000: one ReLU sign flip cannot move a step by 1e-4 there) ends
+    with per-label AUROC / AUPR within 1e-4 of the fp64 oracle's trajectory, probabilities within 1e-4."""
+    import argparse
+    import pickle
+    from scipy import sparse
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from chromegcn_b200 import finetune as ft, synthetic
+    from chromegcn_b200.chrome_models import ChromeGCN
+    from chromegcn_b200.optim import get_optimizer
+    import tempfile
+    nclass = 12
+    h = synthetic.make_hic("chr22", hic_edges=200000)
+    ip, ix = oadj.build_adjacency_numpy(h.window_starts, h.bin1, h.bin2, h.val, h.norm, 1, 200000)
+    n = ip.shape[0] - 1
+    gen = torch.Generator().manual_seed(5)
+    xf = torch.randn(n, 128, generator=gen)
+    xr = xf + 0.2 * torch.randn(n, 128, generator=gen)
+    wtrue = torch.randn(128, nclass, generator=gen)
+    tgt = ((xf @ wtrue) > 8.0).float()                       # learnable labels, a few per cent positives
+    feats = {"chr22": {"forward": xf, "backward": xr, "target": tgt}}
+    tmp = tempfile.mkdtemp()
+    for split in ("train", "valid"):
+        with open(os.path.join(tmp, "%s_graphs_200000_SQRTVCnorm.pkl" % split), "wb") as fp:
+            pickle.dump({"chr22": sparse.csr_matrix((np.ones(ix.shape[0]), ix, ip), shape=(n, n))}, fp)
+    opt = argparse.Namespace(adj_type="hic", graph_root=tmp, hicsize="200000", hicnorm="SQRTVC", optim="sgd", lr=0.25)
+    torch.manual_seed(2)
+    o64 = ogcn.ChromeGCNOracle(128, 128, nclass, 0.0, True, 2)
+    m = ChromeGCN(128, 128, nclass, 0.0, True, 2)
+    m.load_state_dict(o64.state_dict())
+    m = m.to(_dev())
+    assert m.gemm_impl == 0
+    optimizer = get_optimizer(m, opt)
+    o64 = o64.double()
+    oopt = ogcn.make_optimizer(o64, "sgd", 0.25)
+    f64 = {"chr22": {k: v.double() for k, v in feats["chr22"].items()}}
+    ft.clear_caches()
+    for epoch in (1, 2, 3):
+        _, _, l = ft.finetune(None, m, feats, None, optimizer, epoch, None, opt, "train")
+        _, _, l64 = ogcn.finetune_epoch(o64, f64, {"chr22": (ip, ix)}, oopt, "train")
+        assert abs(l - l64) <= 1e-5 * abs(l64), (epoch, l, l64)
+    pv, _, _ = ft.finetune(None, m, feats, None, optimizer, 3, None, opt, "valid")
+    pv64, _, _ = ogcn.finetune_epoch(o64, f64, {"chr22": (ip, ix)}, oopt, "valid")
+    assert float((pv.double() - pv64).abs().max()) <= 1e-4
+    t = tgt.numpy()
+    for c in range(nclass):
+        if 0 < t[:, c].sum() < n:
+            assert abs(roc_auc_score(t[:, c], pv[:, c].numpy()) - roc_auc_score(t[:, c], pv64[:, c].numpy())) <= 1e-4, c
+            assert abs(average_precision_score(t[:, c], pv[:, c].numpy()) - average_precision_score(t[:, c], pv64[:, c].numpy())) <= 1e-4, c
