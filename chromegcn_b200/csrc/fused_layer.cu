@@ -38,10 +38,10 @@ namespace fl {
 using namespace tc;
 
 constexpr int TM = 64;                         // panel rows per tile = UMMA N
-constexpr int EPI_WARPS = 4;                   // warp w <-> TMEM lane quarter w
-constexpr int ISSUE_WARP = EPI_WARPS;          // the first gather warp also issues the MMAs (no dedicated warp: 20 warps =
-                                               // 5 per scheduler leaves 96 registers per thread, 21 would leave 80)
-constexpr int threads_for(int gw) { return (EPI_WARPS + gw) * 32; }
+// Epilogue warps E (4 or 8; warps 0..3 are the ones that read the accumulator, warp w <-> TMEM lane quarter w) come
+// first, then the gather / producer warps; the first of those also issues the MMAs (no dedicated warp).  Registers per
+// thread follow from the warps per scheduler: 20 warps -> 96, 24 warps -> 80.
+constexpr int threads_for(int gw, int e) { return (e + gw) * 32; }
 // Gather warps per CTA: 16 (640 threads, 96 registers, 2 x 4 column indices x strands of loads in flight per warp) or
 // 8 (384 threads, 168 registers, 2 x 8).  CGCN_FUSED_GW selects; both are built.
 constexpr int A_CHUNK = TM * 128;              // one k-chunk (32 floats) of the tile: 64 rows x 128 B = 8 KB
@@ -108,8 +108,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
 }
 
-template <int S, int MODE, int G_WARPS, bool PEER, int SRC>
-__global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(const Args a) {
+template <int S, int MODE, int G_WARPS, bool PEER, int SRC, int E>
+__global__ void __launch_bounds__(threads_for(G_WARPS, E), 1) fused_layer_kernel(const Args a) {
+  constexpr int EPI_WARPS = E, ISSUE_WARP = E;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t sA = base, sY = base + OFF_Y;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + OFF_MISC + 56);
 
-  if (warp < EPI_WARPS && ntile > 0) {
+  if (warp < 4 && ntile > 0) {
     // The weight operand into tensor memory: thread f of the epilogue warps owns TMEM lane f = output feature f and
     // writes A[f][k] = Bw(f, k) (the weight that multiplies input column k into output column f) for k = 0..127,
     // as hi and lo TF32 images.  W is 64 KB and L2 resident; this runs once per CTA while the gather warps already
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
     }
     tmem_wait_st();
     tc_fence_before();
-    named_bar_sync(3, (EPI_WARPS + 1) * 32);
+    named_bar_sync(3, 5 * 32);
     tc_fence_after();
   }
 
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
     auto issue_mma = [&](int t) {
       const uint32_t accb = t & 1;
       if (t == 0) {                                // the weight images are in tensor memory (see above)
-        named_bar_sync(3, (EPI_WARPS + 1) * 32);
+        named_bar_sync(3, 5 * 32);
         tc_fence_after();
       }
       mbar_wait(bar_tempty + 8 * accb, ((t >> 1) & 1) ^ 1);
@@ -429,39 +430,48 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
     // =========================================================== epilogue warps
     // Phase A (thread = output feature: the accumulator is y^T, TMEM lane f = feature f, column r = tile row r):
     // TMEM -> + bias -> row-major shared y tile (one conflict-free 128-byte store per row per warp).
-    // Phase B (8 lanes per row, 4 rows per warp instruction): everything else, on 16 rows per warp.
-    const int sub = lane >> 3, q = lane & 7;
-    constexpr int NST = (MODE == FWD_STATS || MODE == BWD_MID) ? 4 : 1;
+    // Phase B (LPR lanes per row, RPI rows per warp step; lane q owns the float4 column groups cc * CSTRIDE + 4 q):
+    // everything else, on TM / E rows per epilogue warp.  E = 4: 8 lanes per row, 16 values per lane per step;
+    // E = 8: 16 lanes per row, 8 values per lane (fits the 80-register budget of a 24-warp CTA).
+    constexpr int LPR = (E == 4) ? 8 : 16, RPI = 32 / LPR, CPL = 32 / LPR, CSTRIDE = LPR * 4;
+    constexpr int ROWS_W = TM / E, ITERS = ROWS_W / RPI;
+    static_assert(CPL * CSTRIDE == 128 && ITERS >= 1 && ROWS_W % 2 == 0 && E * RPI == 16, "epilogue split");
+    const int sub = lane / LPR, q = lane % LPR;
+    constexpr int NST = (MODE == FWD_STATS || MODE == BWD_MID) ? CPL : 1;
     float4 st0[NST], st1[NST];                     // FWD_STATS: sum / sum of squares of relu(x') ; BWD_MID: d b / d w_g
     float st2 = 0.f;                               // BWD_MID: d b_g
 #pragma unroll
     for (int i = 0; i < NST; ++i) st0[i] = st1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float bg = (FORWARD && !a.gate_off) ? __ldg(a.bg) : 0.f;
     float bias_f = 0.f;                            // threadIdx.x = this thread's feature
-    if (FORWARD) bias_f = __ldg(a.bias + threadIdx.x);
+    if (FORWARD && threadIdx.x < 128) bias_f = __ldg(a.bias + threadIdx.x);
     if (MODE == HEAD_FWD && static_cast<int>(threadIdx.x) < a.w_rows) bias_f = __ldg(a.bias + threadIdx.x);
     const int64_t prow_end = static_cast<int64_t>(r_end) * S;
 
     for (int t = 0; t < ntile; ++t) {
       const uint32_t accb = t & 1;
-      mbar_wait(bar_tfull + 8 * accb, (t >> 1) & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + TM_ACC + accb * 64 + half * 32, r);
-        float* yrow = reinterpret_cast<float*>(smem_raw + OFF_Y) + (half * 32) * 128 + threadIdx.x;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) yrow[j * 128] = __uint_as_float(r[j]) + bias_f;
+      if (warp < 4) {
+        mbar_wait(bar_tfull + 8 * accb, (t >> 1) & 1);
+        tc_fence_after();
       }
-      tc_fence_before();
-      named_bar_sync(2, EPI_WARPS * 32);           // the y tile is complete (every warp wrote 32 features of every row)
+      if (warp < 4) {                              // the four warps that can read the accumulator's 128 lanes
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + TM_ACC + accb * 64 + half * 32, r);
+          float* yrow = reinterpret_cast<float*>(smem_raw + OFF_Y) + (half * 32) * 128 + threadIdx.x;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) yrow[j * 128] = __uint_as_float(r[j]) + bias_f;
+        }
+        tc_fence_before();
+      }
+      named_bar_sync(2, E * 32);                   // the y tile is complete (every warp wrote 32 features of every row)
       if (threadIdx.x == 0) mbar_arrive(bar_tempty + 8 * accb);            // accumulator released before the heavy phase
 
       const int64_t tile_prow0 = (static_cast<int64_t>(r_begin) + static_cast<int64_t>(t) * TG) * S;
 #pragma unroll 1
-      for (int it = 0; it < 4; ++it) {
-        const int pr = 16 * warp + it * 4 + sub;
+      for (int it = 0; it < ITERS; ++it) {
+        const int pr = ROWS_W * warp + it * RPI + sub;
         const int64_t grow = tile_prow0 + pr;      // panel row (local)
         const bool valid = grow < prow_end;
         const size_t gofs = static_cast<size_t>(grow) * 128 + 4 * q;
@@ -469,55 +479,56 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
           // L1 prefetch of the NEXT step's streamed operands (next 4 rows of this warp; the first 4 of the next tile
           // after the last step): the epilogue warps have no registers to spare for a software pipeline, and without
           // this every step starts with a full L2 / DRAM round trip (3 panels in the backward mode).
-          const int64_t nrow_p = (it < 3) ? grow + 4 : grow + (TM - 12);
+          const int64_t nrow_p = (it < ITERS - 1) ? grow + RPI : grow + (TM - (ITERS - 1) * RPI);
           if (nrow_p < prow_end) {
             const size_t nofs = static_cast<size_t>(nrow_p) * 128 + 4 * q;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < CPL; ++cc) {
               if constexpr (FORWARD) {
-                prefetch_l1(a.xin + nofs + cc * 32);
+                prefetch_l1(a.xin + nofs + cc * CSTRIDE);
               } else if constexpr (MODE != HEAD_FWD) {
-                prefetch_l1(a.dxd_in + nofs + cc * 32);
+                prefetch_l1(a.dxd_in + nofs + cc * CSTRIDE);
                 if constexpr (MODE == BWD_MID) {
-                  prefetch_l1(a.z_prev + nofs + cc * 32);
-                  prefetch_l1(a.x_prev + nofs + cc * 32);
+                  prefetch_l1(a.z_prev + nofs + cc * CSTRIDE);
+                  prefetch_l1(a.x_prev + nofs + cc * CSTRIDE);
                 }
               }
             }
           }
         }
-        float4 y[4];
+        float4 y[CPL];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) y[cc] = lds_f4(sY + pr * 512 + (cc * 32 + 4 * q) * 4);
+        for (int cc = 0; cc < CPL; ++cc) y[cc] = lds_f4(sY + pr * 512 + (cc * CSTRIDE + 4 * q) * 4);
 
         if constexpr (FORWARD) {
-          float4 xv[4];
+          float4 xv[CPL];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) xv[cc] = valid ? ldg4(a.xin + gofs + cc * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int cc = 0; cc < CPL; ++cc) xv[cc] = valid ? ldg4(a.xin + gofs + cc * CSTRIDE) : make_float4(0.f, 0.f, 0.f, 0.f);
           float dot = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const float4 w = lds_f4(sVec1 + (cc * 32 + 4 * q) * 4);
+          for (int cc = 0; cc < CPL; ++cc) {
+            const float4 w = lds_f4(sVec1 + (cc * CSTRIDE + 4 * q) * 4);
             y[cc] = make_float4(tanhf(y[cc].x), tanhf(y[cc].y), tanhf(y[cc].z), tanhf(y[cc].w));
             dot += y[cc].x * w.x + y[cc].y * w.y + y[cc].z * w.z + y[cc].w * w.w;
           }
           dot += __shfl_xor_sync(0xffffffffu, dot, 1);
           dot += __shfl_xor_sync(0xffffffffu, dot, 2);
           dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+          if (LPR == 16) dot += __shfl_xor_sync(0xffffffffu, dot, 8);
           const float g = a.gate_off ? 1.0f : sigmoidf_(dot + bg);
           const float omg = 1.0f - g;
           if (valid) {
             if (q == 0) a.g[grow] = g;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < CPL; ++cc) {
               float4 h = make_float4(omg * xv[cc].x + g * y[cc].x, omg * xv[cc].y + g * y[cc].y, omg * xv[cc].z + g * y[cc].z,
                                      omg * xv[cc].w + g * y[cc].w);
               if (a.drop.enabled) {
-                const float4 m = dropout_mult4(a.drop, (gofs + cc * 32) >> 2);
+                const float4 m = dropout_mult4(a.drop, (gofs + cc * CSTRIDE) >> 2);
                 h = make_float4(h.x * m.x, h.y * m.y, h.z * m.z, h.w * m.w);
               }
-              st4(a.z + gofs + cc * 32, y[cc]);
-              st4(a.xo + gofs + cc * 32, h);
+              st4(a.z + gofs + cc * CSTRIDE, y[cc]);
+              st4(a.xo + gofs + cc * CSTRIDE, h);
               if constexpr (MODE == FWD_STATS) {
                 const float4 rl = make_float4(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f), fmaxf(h.z, 0.f), fmaxf(h.w, 0.f));
                 st0[cc].x += rl.x; st0[cc].y += rl.y; st0[cc].z += rl.z; st0[cc].w += rl.w;
@@ -528,19 +539,19 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
         } else if constexpr (MODE == HEAD_FWD) {     // logits: the first out_ld columns of the row (bias added in phase A)
           if (valid) {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              if (cc * 32 + 4 * q < a.out_ld) st4(a.out + static_cast<size_t>(grow) * a.out_ld + cc * 32 + 4 * q, y[cc]);
+            for (int cc = 0; cc < CPL; ++cc)
+              if (cc * CSTRIDE + 4 * q < a.out_ld) st4(a.out + static_cast<size_t>(grow) * a.out_ld + cc * CSTRIDE + 4 * q, y[cc]);
           }
         } else if constexpr (MODE == BWD_INPUT) {
           if (valid) {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const float4 e = ldg4(a.dxd_in + gofs + cc * 32);
-              st4(a.dx_out + gofs + cc * 32, make_float4(y[cc].x + e.x, y[cc].y + e.y, y[cc].z + e.z, y[cc].w + e.w));
+            for (int cc = 0; cc < CPL; ++cc) {
+              const float4 e = ldg4(a.dxd_in + gofs + cc * CSTRIDE);
+              st4(a.dx_out + gofs + cc * CSTRIDE, make_float4(y[cc].x + e.x, y[cc].y + e.y, y[cc].z + e.z, y[cc].w + e.w));
             }
           }
         } else {                                   // BWD_MID: gate / tanh backward of layer l-1 on dx = u W^T + (1-g_l) dh_l
-          float4 zv[4];
+          float4 zv[CPL];
           float part = 0.f;
           // scalar operands of the row first: their latency overlaps the panel loads instead of following the reduction
           float g = 1.0f;
@@ -551,17 +562,17 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
             deg = __ldg(a.rowptr + wr + 1) - __ldg(a.rowptr + wr);
           }
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
+          for (int cc = 0; cc < CPL; ++cc) {
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f), xv = e;
             zv[cc] = e;
             if (valid) {
-              e = ld4(a.dxd_in + gofs + cc * 32);  // may alias dxd_out: plain load, same lane reads then writes
-              zv[cc] = ldg4(a.z_prev + gofs + cc * 32);
-              xv = ldg4(a.x_prev + gofs + cc * 32);
+              e = ld4(a.dxd_in + gofs + cc * CSTRIDE);  // may alias dxd_out: plain load, same lane reads then writes
+              zv[cc] = ldg4(a.z_prev + gofs + cc * CSTRIDE);
+              xv = ldg4(a.x_prev + gofs + cc * CSTRIDE);
             }
             float4 d = make_float4(y[cc].x + e.x, y[cc].y + e.y, y[cc].z + e.z, y[cc].w + e.w);
             if (a.drop.enabled) {
-              const float4 m = dropout_mult4(a.drop, (gofs + cc * 32) >> 2);
+              const float4 m = dropout_mult4(a.drop, (gofs + cc * CSTRIDE) >> 2);
               d = make_float4(d.x * m.x, d.y * m.y, d.z * m.z, d.w * m.w);
             }
             y[cc] = d;
@@ -570,20 +581,21 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
           part += __shfl_xor_sync(0xffffffffu, part, 1);
           part += __shfl_xor_sync(0xffffffffu, part, 2);
           part += __shfl_xor_sync(0xffffffffu, part, 4);
+          if (LPR == 16) part += __shfl_xor_sync(0xffffffffu, part, 8);
           if (valid) {
             const float dgp = a.gate_off ? 0.0f : part * g * (1.0f - g);
             const float omg = 1.0f - g;
             const float inv = deg > 0 ? __fdiv_rn(1.0f, static_cast<float>(deg)) : 0.0f;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const float4 w = lds_f4(sVec1 + (cc * 32 + 4 * q) * 4);
+            for (int cc = 0; cc < CPL; ++cc) {
+              const float4 w = lds_f4(sVec1 + (cc * CSTRIDE + 4 * q) * 4);
               const float4 dz = make_float4(g * y[cc].x + dgp * w.x, g * y[cc].y + dgp * w.y, g * y[cc].z + dgp * w.z,
                                             g * y[cc].w + dgp * w.w);
               const float4 dy = make_float4(dz.x * (1.0f - zv[cc].x * zv[cc].x), dz.y * (1.0f - zv[cc].y * zv[cc].y),
                                             dz.z * (1.0f - zv[cc].z * zv[cc].z), dz.w * (1.0f - zv[cc].w * zv[cc].w));
-              st4(a.dys_out + gofs + cc * 32, make_float4(dy.x * inv, dy.y * inv, dy.z * inv, dy.w * inv));
+              st4(a.dys_out + gofs + cc * CSTRIDE, make_float4(dy.x * inv, dy.y * inv, dy.z * inv, dy.w * inv));
               if (a.dxd_out != nullptr)
-                st4(a.dxd_out + gofs + cc * 32, make_float4(omg * y[cc].x, omg * y[cc].y, omg * y[cc].z, omg * y[cc].w));
+                st4(a.dxd_out + gofs + cc * CSTRIDE, make_float4(omg * y[cc].x, omg * y[cc].y, omg * y[cc].z, omg * y[cc].w));
               st0[cc].x += dy.x; st0[cc].y += dy.y; st0[cc].z += dy.z; st0[cc].w += dy.w;
               st1[cc].x += dgp * zv[cc].x; st1[cc].y += dgp * zv[cc].y; st1[cc].z += dgp * zv[cc].z; st1[cc].w += dgp * zv[cc].w;
             }
@@ -591,21 +603,22 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
           }
         }
       }
-      named_bar_sync(2, EPI_WARPS * 32);           // everybody is done reading the y tile
+      named_bar_sync(2, E * 32);                   // everybody is done reading the y tile
     }
 
     // ---- column partials of this CTA, fixed order: (warp, row slot) pairs summed per column by 128 threads
     if constexpr (MODE == FWD_STATS || MODE == BWD_MID) {
       float* red = reinterpret_cast<float*>(smem_raw + OFF_Y);      // [2][16 slots][128 cols] (+ 16 floats)
-      const int slot = warp * 4 + sub;
+      const int slot = warp * RPI + sub;           // 16 slots; a slot always sees the same strand (slot & 1)
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        *reinterpret_cast<float4*>(red + (0 * 16 + slot) * 128 + cc * 32 + 4 * q) = st0[cc];
-        *reinterpret_cast<float4*>(red + (1 * 16 + slot) * 128 + cc * 32 + 4 * q) = st1[cc];
+      for (int cc = 0; cc < CPL; ++cc) {
+        *reinterpret_cast<float4*>(red + (0 * 16 + slot) * 128 + cc * CSTRIDE + 4 * q) = st0[cc];
+        *reinterpret_cast<float4*>(red + (1 * 16 + slot) * 128 + cc * CSTRIDE + 4 * q) = st1[cc];
       }
       if (MODE == BWD_MID && q == 0) red[2 * 16 * 128 + slot] = st2;
-      named_bar_sync(1, EPI_WARPS * 32);
-      const int c = threadIdx.x;                   // 0..127: one column each
+      named_bar_sync(1, E * 32);
+      const int c = threadIdx.x;                   // 0..127: one column each (the other epilogue threads are done)
+      if (c < 128) {
       if constexpr (MODE == FWD_STATS) {
         // slot's strand: panel rows alternate strands and a slot always sees the same parity (S == 2: sub & 1)
         float* dst = a.partial + static_cast<size_t>(blockIdx.x) * (2 * S * 128);
@@ -636,6 +649,7 @@ __global__ void __launch_bounds__(threads_for(G_WARPS), 1) fused_layer_kernel(co
             for (int sl = 0; sl < 16; ++sl) t2 += red[2 * 16 * 128 + sl];
           dst[256 + c] = t2;
         }
+      }
       }
     }
   }
@@ -681,20 +695,23 @@ int fused_layer_launch(fl::Args a, int S, int mode, int* grid_out, cudaStream_t 
   const int src = a.source;
   CGCN_REQUIRE(!(peer && src != fl::GATHER), "fused layer: peer panels are gathered, not streamed");
   CGCN_REQUIRE((mode == fl::HEAD_FWD) == (src == fl::STREAM_BN), "fused layer: HEAD_FWD goes with STREAM_BN");
-#define FL_LAUNCH(SV, MV, GV, PV, RV)                                                                                \
-  if (S == SV && mode == MV && gwsel == GV && peer == PV && src == RV) {                                             \
+#define FL_LAUNCH(SV, MV, GV, PV, RV, EV)                                                                            \
+  if (S == SV && mode == MV && gwsel == GV && peer == PV && src == RV && esel == EV) {                               \
     static bool attr_set[64] = {};                                                                                   \
     if (first_use_on_device(attr_set))                                                                               \
-      CGCN_CUDA(cudaFuncSetAttribute(fl::fused_layer_kernel<SV, MV, GV, PV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::SMEM)); \
-    CGCN_CUDA(launch_k(fl::fused_layer_kernel<SV, MV, GV, PV, RV>, dim3(grid), dim3(fl::threads_for(GV)), fl::SMEM, stream, a)); \
+      CGCN_CUDA(cudaFuncSetAttribute(fl::fused_layer_kernel<SV, MV, GV, PV, RV, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::SMEM)); \
+    CGCN_CUDA(launch_k(fl::fused_layer_kernel<SV, MV, GV, PV, RV, EV>, dim3(grid), dim3(fl::threads_for(GV, EV)), fl::SMEM, stream, a)); \
     return check_launch("fused_layer_kernel");                                                                      \
   }
   const int gwsel = (src == fl::GATHER) ? gw : 16;
-#define FL_MODES(SV, GV, PV, RV) \
-  FL_LAUNCH(SV, fl::FWD, GV, PV, RV) FL_LAUNCH(SV, fl::FWD_STATS, GV, PV, RV) FL_LAUNCH(SV, fl::BWD_MID, GV, PV, RV) FL_LAUNCH(SV, fl::BWD_INPUT, GV, PV, RV)
-#define FL_STRANDS(SV)                                                                                   \
-  FL_MODES(SV, 16, false, fl::GATHER) FL_MODES(SV, 16, true, fl::GATHER) FL_MODES(SV, 8, false, fl::GATHER) \
-  FL_MODES(SV, 16, false, fl::STREAM) FL_LAUNCH(SV, fl::HEAD_FWD, 16, false, fl::STREAM_BN)
+  static const int e_env = getenv("CGCN_FUSED_EPI") != nullptr ? atoi(getenv("CGCN_FUSED_EPI")) : 4;
+  const int esel = (gwsel == 16 && !peer && e_env == 8) ? 8 : 4;
+#define FL_MODES(SV, GV, PV, RV, EV) \
+  FL_LAUNCH(SV, fl::FWD, GV, PV, RV, EV) FL_LAUNCH(SV, fl::FWD_STATS, GV, PV, RV, EV) FL_LAUNCH(SV, fl::BWD_MID, GV, PV, RV, EV) FL_LAUNCH(SV, fl::BWD_INPUT, GV, PV, RV, EV)
+#define FL_STRANDS(SV)                                                                                              \
+  FL_MODES(SV, 16, false, fl::GATHER, 4) FL_MODES(SV, 16, false, fl::GATHER, 8) FL_MODES(SV, 16, true, fl::GATHER, 4) \
+  FL_MODES(SV, 8, false, fl::GATHER, 4) FL_MODES(SV, 16, false, fl::STREAM, 4) FL_MODES(SV, 16, false, fl::STREAM, 8) \
+  FL_LAUNCH(SV, fl::HEAD_FWD, 16, false, fl::STREAM_BN, 4) FL_LAUNCH(SV, fl::HEAD_FWD, 16, false, fl::STREAM_BN, 8)
   FL_STRANDS(1)
   FL_STRANDS(2)
 #undef FL_LAUNCH
