@@ -56,8 +56,13 @@ def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> None:
 
 def default_rounds(n_items: int, world: int) -> int:
     """Optimiser steps per pass over the chromosomes: one per chromosome on one rank (the reference,
-    finetune.py:39-49); `n_items // world` on several (each step then consumes about `world` chromosomes)."""
-    return n_items if world <= 1 else max(1, n_items // world)
+    finetune.py:39-49); ONE on several ranks: every rank walks its LPT share of the chromosomes accumulating
+    gradients, one all-reduce, one step on the mean gradient of the whole pass.  Lock-step rounds cost
+    sum_r max_rank load(r, rank); with 23 chromosomes over 8 ranks the packing granularity makes that 0.89 of
+    the balanced pass for 2 rounds, 0.84 for 3, against 0.955 for a single round (chr1 alone is 8.2 % of the genome),
+    measured 0.84 / 0.9x on 8 B200 (profiles/).  `balanced_schedule(..., rounds=k)` / `bench.py --rounds k` give the
+    grouped variants (k = n_items // world keeps "about `world` chromosomes per step")."""
+    return n_items if world <= 1 else 1
 
 
 def balanced_schedule(costs: Dict[str, float], world: int, rounds: int = None) -> List[List[List[str]]]:
