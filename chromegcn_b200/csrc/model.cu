@@ -373,6 +373,14 @@ static int layer_mode(const cgcn_model* m) {
   return nnz <= static_cast<int64_t>(max_deg) * n ? 1 : 0;
 }
 static bool use_fused(const cgcn_model* m) { return layer_mode(m) != 0; }
+// The backward twin of the fused kernel (gather -> W^T -> + (1-g) dh -> gate backward of the layer below) measures the
+// same as row-panel contraction + SpMM + gate kernel on the fused forward's conventions (15.7 ms per whole-genome pass
+// either way: it is bound by its four epilogue warps streaming three panels); it is the default because it moves 5
+// panels instead of 9.  CGCN_BWD_UNFUSED=1 selects the three kernels.
+static bool use_fused_bwd(const cgcn_model* m) {
+  static const bool off = getenv("CGCN_BWD_UNFUSED") != nullptr;
+  return !off && use_fused(m);
+}
 
 static int prep_fwd_images(const Ctx& c) {
   pdl_plain_next(c.st);              // first kernel of a pass: ordinary stream order against whatever ran before
@@ -709,7 +717,7 @@ static int bwd_layer_fused(const Ctx& c, Fork& f, int l, int parts, const float*
 
 // gate stage of layer l, its weight gradients (side stream) and, if anything upstream needs it, t = D^-1 (dy W^T).
 // Returns in *t_out the panel holding t (NULL if the chain stops here).
-static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out) {
+static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out, bool dys = false) {
   const cgcn_model* m = c.m;
   const WsLayout& lay = c.lay;
   float* ws = c.ws;
@@ -738,6 +746,9 @@ static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out) {
   a.partial = ws + lay.partial_l[l];
   a.n = c.n;
   a.drop = make_dropout(m->dropout_p, m->seed, m->step, head ? 1 : layer_drop_site(l), m->training, c.drop_off);
+  // dys: the forward pass was fused (saved panels hold the UN-normalised sums), so dy is stored as D^-1 dy: the weight
+  // gradient ax^T dy keeps its value and the contraction below needs no row scale ((D^-1 dy) W^T = D^-1 (dy W^T))
+  a.scale_rowptr = dys ? m->graph.rowptr : nullptr;
   int grid = 0;
   CGCN_TRY(gate_bwd_launch(a, c.d, c.S, head, &grid, c.st));
   // side: bias / gate gradients from the partials, d W = (A_hat x)^T dy
@@ -747,8 +758,8 @@ static int bwd_layer(const Ctx& c, Fork& f, int l, const float** t_out) {
                               lay.gram_bytes, f.ss));
   if (!need_dx) return CGCN_OK;
   // main: t = D^-1 (dy W^T) -> the panel that held `src`
-  CGCN_TRY(gemm_rowpanel_dispatch(dy, c.d, m->params.gc_w[l], 1, nullptr, src, c.d, c.M, c.d, c.d, m->graph.rowptr, m->graph.row_inv, c.S,
-                                  m->gemm_impl, c.tcws, lay.tc_bytes, c.st, bwd_image(c, 1 + l)));
+  CGCN_TRY(gemm_rowpanel_dispatch(dy, c.d, m->params.gc_w[l], 1, nullptr, src, c.d, c.M, c.d, c.d, dys ? nullptr : m->graph.rowptr,
+                                  dys ? nullptr : m->graph.row_inv, c.S, m->gemm_impl, c.tcws, lay.tc_bytes, c.st, bwd_image(c, 1 + l)));
   *t_out = src;
   return CGCN_OK;
 }
@@ -760,7 +771,8 @@ static int model_backward(const cgcn_model* m) {
   Fork f;
   CGCN_TRY(make_fork(c, &f));
   CGCN_TRY(bwd_head(c, f));
-  if (use_fused(m)) {
+  const bool dys = use_fused(m);
+  if (use_fused_bwd(m)) {
     int parts = 0;
     for (int l = c.L - 1; l >= 0; --l) {
       const float* t = nullptr;
@@ -772,7 +784,7 @@ static int model_backward(const cgcn_model* m) {
   }
   for (int l = c.L - 1; l >= 0; --l) {
     const float* t = nullptr;
-    CGCN_TRY(bwd_layer(c, f, l, &t));
+    CGCN_TRY(bwd_layer(c, f, l, &t, dys));
     if (t == nullptr) break;
     CGCN_TRY(bwd_propagate(c, l, t));
   }
@@ -807,19 +819,19 @@ static int model_phase(const cgcn_model* m, int kind, int layer, const float** p
     case CGCN_PHASE_BWD_HEAD:
       return bwd_head(c, f);
     case CGCN_PHASE_BWD_LAYER:       // layer == L-1: bn_sums all-reduced ; else: x_full holds the gathered t of layer+1
-      if (use_fused(m)) {
+      if (use_fused_bwd(m)) {
         int parts = 0;
         if (layer < c.L - 1) CGCN_TRY(bwd_propagate_fused(c, layer + 1, m->x_full, &parts));
         CGCN_TRY(bwd_layer_fused(c, f, layer, parts, &t));
       } else {
         if (layer < c.L - 1) CGCN_TRY(bwd_propagate(c, layer + 1, m->x_full));
-        CGCN_TRY(bwd_layer(c, f, layer, &t));
+        CGCN_TRY(bwd_layer(c, f, layer, &t, use_fused(m)));
       }
       if (publish) *publish = t;
       return CGCN_OK;
     case CGCN_PHASE_BWD_INPUT:       // x_full holds the gathered t of layer 0
       CGCN_REQUIRE(m->need_input_grad && m->x_in_grad, "cgcn_model_phase: BWD_INPUT without need_input_grad");
-      if (use_fused(m)) return bwd_propagate_fused(c, 0, m->x_full, nullptr);
+      if (use_fused_bwd(m)) return bwd_propagate_fused(c, 0, m->x_full, nullptr);
       return bwd_propagate(c, 0, m->x_full);
     default:
       set_error("cgcn_model_phase: unknown phase %d", kind);

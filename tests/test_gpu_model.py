@@ -652,3 +652,22 @@ def test_three_epoch_trajectory_on_a_chr22_sized_graph_keeps_per_label_auroc_aup
         if 0 < t[:, c].sum() < n:
             assert abs(roc_auc_score(t[:, c], pv[:, c].numpy()) - roc_auc_score(t[:, c], pv64[:, c].numpy())) <= 1e-4, c
             assert abs(average_precision_score(t[:, c], pv[:, c].numpy()) - average_precision_score(t[:, c], pv64[:, c].numpy())) <= 1e-4, c
+
+
+@pytest.mark.parametrize("env", [{"CGCN_BWD_UNFUSED": "1"}, {"CGCN_FUSED_EPI": "8"},
+                                 {"CGCN_LAYER_MODE": "stream", "CGCN_FUSED_HEAD": "1"},
+                                 {"CGCN_LAYER_MODE": "unfused"}, {"CGCN_FUSED_GW": "8"}],
+                         ids=["bwd_unfused", "epi8", "stream_head", "unfused", "gw8"])
+def test_alternative_kernel_paths_keep_parity(env):
+    """The library picks its layer kernels once per process (static switches: all-in-one gather kernel, SpMM + streamed
+    contraction kernel, the three-kernel path, the fused backward twin, the fused head, 8 epilogue / 8 gather warps).  The
+    default is whatever measured fastest; the others must stay correct: the model parity tests re-run in a subprocess
+    under each setting."""
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "fused_engine_matches_reference or module_api_matches_reference or extension_variants or dropout_training"],
+                       capture_output=True, text=True, timeout=900, env=e, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
