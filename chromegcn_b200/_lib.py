@@ -70,6 +70,7 @@ PROTOTYPES = {
     "cgcn_coo_to_pattern_workspace_bytes": (C.c_int, [_I64, _I64, C.POINTER(_SZ)]),
     "cgcn_coo_to_pattern": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, C.POINTER(_I32), _P, _SZ, _P]),
     "cgcn_spmm": (C.c_int, [C.POINTER(Graph), _P, _P, _I32, _I32, _P, _P]),
+    "cgcn_sddmm": (C.c_int, [C.POINTER(Graph), _P, _P, _I32, _P, _P]),
     "cgcn_spmm_peer": (C.c_int, [C.POINTER(Graph), C.POINTER(PeerPanel), _P, _I32, _I32, _P, _P]),
     "cgcn_peer_alloc": (C.c_int, [_SZ, C.POINTER(_P), C.c_char_p]),
     "cgcn_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),

@@ -60,8 +60,7 @@ def _as_graph(adj, cache: Dict) -> HiCGraph:
                 cache.clear()
             cache[key] = g
         return g
-    raise NotImplementedError("adj must be a HiCGraph or a torch sparse COO tensor (dense / arbitrary adjacency "
-                              "matrices, e.g. the A-saliency script, are not on the CUDA path)")
+    raise TypeError("adj must be a HiCGraph or a torch tensor (sparse COO or dense)")
 
 
 class _GraphConvFn(torch.autograd.Function):
@@ -293,14 +292,29 @@ class ChromeGCN(nn.Module):
         self._drop_step += 1
         return self._drop_seed, self._drop_step
 
-    def resolve_graph(self, adj) -> HiCGraph:
-        return _as_graph(adj, self._graph_cache)
+    def resolve_graph(self, adj) -> Optional[HiCGraph]:
+        """The pattern graph behind `adj`, or None when `adj` needs the generic path (generic_adj.py)."""
+        if isinstance(adj, torch.Tensor) and (adj.layout == torch.strided or adj.requires_grad):
+            return None
+        try:
+            return _as_graph(adj, self._graph_cache)
+        except NotImplementedError:
+            if isinstance(adj, torch.Tensor):
+                return None
+            raise
 
     def forward(self, x_in, adj, deg=None, src_dict=None, return_gate=False):
         _lib.require_cuda()
         if not (isinstance(x_in, torch.Tensor) and x_in.is_cuda):
             raise _lib.ChromeGCNNativeError("ChromeGCN.forward needs CUDA inputs (no CPU fallback)")
         graph = self.resolve_graph(adj)
+        if graph is None:
+            # dense `adj`, `adj` that requires grad, or a sparse tensor that is not a symmetric mean-aggregation pattern
+            # (scripts/visualize.py:30-45,103-111): the generic weighted-CSR path with d loss / d adj
+            from .generic_adj import forward_generic
+            out, gates = forward_generic(self, x_in, adj)
+            self.last_gates = list(gates)
+            return x_in, out, (gates[0], gates[1] if self.num_layers >= 2 else None), None
         res = _ChromeGCNFn.apply(x_in, self, graph, *self._param_tensors())
         out, g = res[0], res[1]
         g2 = res[2] if self.num_layers >= 2 else None

@@ -367,6 +367,61 @@ static int ipc_alloc(size_t bytes, void** ptr, unsigned char* handle) {
   return CGCN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SDDMM over the stored pattern: out[e] = sum_c G[row(e), c] * S[col(e), c] for every stored entry e (CSR order) --
+// the gradient of  Y = A S  with respect to the VALUES of A (d loss / d a_ij = <G_i, S_j>), which the A-saliency
+// analysis of the reference (scripts/visualize.py:30-45: adj.requires_grad, |adj * adj.grad|) asks for.  Warp per row:
+// the row of G stays in registers, one gathered row of S per stored entry, warp-reduced dot product.
+template <int VEC>
+__global__ void __launch_bounds__(SPMM_WARPS * 32) sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                                int n, const float* __restrict__ G, const float* __restrict__ S,
+                                                                float* __restrict__ out) {
+  constexpr size_t PITCH = static_cast<size_t>(VEC) * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  float4 g[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) g[q] = ldg4(G + static_cast<size_t>(row) * PITCH + q * 128 + lane * 4);
+  for (int base = start; base < end; base += 32) {
+    const int mine = (base + lane < end) ? __ldg(colidx + base + lane) : 0;
+    const int cnt = min(32, end - base);
+    float keep = 0.f;
+    for (int k = 0; k < cnt; ++k) {
+      const int c = __shfl_sync(0xffffffffu, mine, k);
+      const float* p = S + static_cast<size_t>(c) * PITCH + lane * 4;
+      float d = 0.f;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        const float4 v = ldg4(p + q * 128);
+        d += g[q].x * v.x + g[q].y * v.y + g[q].z * v.z + g[q].w * v.w;
+      }
+      d = warp_sum(d);
+      if (lane == k) keep = d;
+    }
+    if (lane < cnt) out[base + lane] = keep;
+  }
+}
+
+int sddmm_launch(const cgcn_graph* g, const float* G, const float* S, int width, float* out, cudaStream_t stream) {
+  CGCN_REQUIRE(g != nullptr && g->rowptr != nullptr && (g->colidx != nullptr || g->nnz == 0), "cgcn_sddmm: null graph");
+  CGCN_REQUIRE(G != nullptr && S != nullptr && (out != nullptr || g->nnz == 0), "cgcn_sddmm: null operand");
+  CGCN_REQUIRE(width > 0 && width % 128 == 0 && width <= 1024, "cgcn_sddmm: width %d must be a multiple of 128, <= 1024", width);
+  if (g->n <= 0 || g->nnz <= 0) return CGCN_OK;
+  const dim3 grid((g->n + SPMM_WARPS - 1) / SPMM_WARPS), block(SPMM_WARPS * 32);
+  switch (width / 128) {
+    case 1: sddmm_kernel<1><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, G, S, out); break;
+    case 2: sddmm_kernel<2><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, G, S, out); break;
+    case 4: sddmm_kernel<4><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, G, S, out); break;
+    case 8: sddmm_kernel<8><<<grid, block, 0, stream>>>(g->rowptr, g->colidx, g->n, G, S, out); break;
+    default:
+      set_error("cgcn_sddmm: unsupported width %d (128, 256, 512 or 1024)", width);
+      return CGCN_ERR_INVALID;
+  }
+  return check_launch("sddmm_kernel");
+}
+
 int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int scale_mode, const float* residual,
                 cudaStream_t stream) {
   CGCN_REQUIRE(g != nullptr && g->rowptr != nullptr && (g->colidx != nullptr || g->nnz == 0), "cgcn_spmm: null graph");
@@ -408,6 +463,10 @@ int spmm_launch(const cgcn_graph* g, const float* x, float* out, int width, int 
 extern "C" int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, int32_t scale_mode,
                          const float* residual, cgcn_stream_t stream) {
   return cgcn::spmm_launch(g, x, out, width, scale_mode, residual, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cgcn_sddmm(const cgcn_graph* g, const float* G, const float* S, int32_t width, float* out_vals, cgcn_stream_t stream) {
+  return cgcn::sddmm_launch(g, G, S, width, out_vals, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cgcn_spmm_peer(const cgcn_graph* g, const cgcn_peer_panel* panel, float* out, int32_t width, int32_t scale_mode,

@@ -155,6 +155,15 @@ typedef struct cgcn_graph {
 int cgcn_spmm(const cgcn_graph* g, const float* x, float* out, int32_t width, int32_t scale_mode,
               const float* residual, cgcn_stream_t stream);
 
+/*
+ * Gradient of Y = A X with respect to the stored VALUES of A:  out_vals[e] = <G[row(e), :], S[col(e), :]>  for every
+ * stored entry e in CSR order (an SDDMM over the pattern).  With cgcn_spmm on a graph that carries `vals` (scale_mode 0,
+ * row_inv all ones) this is the generic weighted aggregation + its adjacency gradient that the reference's A-saliency
+ * analysis needs (scripts/visualize.py:30-45: dense `adj` with requires_grad, then |adj * adj.grad|; :103-111: re-normalised,
+ * asymmetric sparse `adj2`).  width = floats per row of G and S (multiple of 128).
+ */
+int cgcn_sddmm(const cgcn_graph* g, const float* G, const float* S, int32_t width, float* out_vals, cgcn_stream_t stream);
+
 /* ------------------------------------- piece 2b: peer-memory SpMM (one graph over several GPUs) ---- */
 /*
  * One graph row-partitioned over the GPUs of one NVLink / NVSwitch box (BASELINE.json configs[3]; the reference

@@ -671,3 +671,49 @@ def test_alternative_kernel_paths_keep_parity(env):
                         "fused_engine_matches_reference or module_api_matches_reference or extension_variants or dropout_training"],
                        capture_output=True, text=True, timeout=900, env=e, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+def test_dense_and_asymmetric_adjacency_with_adjacency_gradient():
+    """scripts/visualize.py:30-45 hands the model a DENSE `adj` that requires grad and reads `|adj * adj.grad|`;
+    :103-111 hands it re-normalised sparse tensors with masked entries (arbitrary values, asymmetric pattern).  Both run
+    on the generic weighted-CSR path (cgcn_spmm with values, its transpose, cgcn_sddmm for d loss / d adj) and must
+    match the reference model (oracle restatement, fp64 CPU) on outputs, parameter gradients and the adjacency
+    gradient on the non-zero support."""
+    from chromegcn_b200.chrome_models import ChromeGCN
+    n, nclass = 300, 7
+    gen = torch.Generator().manual_seed(8)
+    dense = (torch.rand(n, n, generator=gen) < 0.03).float() * torch.rand(n, n, generator=gen)      # asymmetric, weighted
+    dense = dense + torch.eye(n)
+    dense = dense / dense.sum(1, keepdim=True)
+    x = torch.randn(n, 128, generator=gen)
+    tgt = (torch.rand(n, nclass, generator=gen) < 0.2).double()
+    torch.manual_seed(3)
+    om = ogcn.stress_init_(ogcn.ChromeGCNOracle(128, 128, nclass, 0.0, True, 2)).double().train()
+    m = ChromeGCN(128, 128, nclass, 0.0, True, 2)
+    m.load_state_dict({k: v.float() for k, v in om.state_dict().items()})
+    m = m.to(_dev()).train()
+    # ---- dense adj with requires_grad
+    a_ref = dense.double().clone().requires_grad_(True)
+    _, out_ref, gates_ref, _ = om(x.double(), a_ref, None)
+    torch.sigmoid(out_ref).backward(gradient=tgt)
+    a = dense.to(_dev()).clone().requires_grad_(True)
+    _, out, gates, _ = m(x.to(_dev()), a, None)
+    torch.sigmoid(out).backward(gradient=tgt.float().to(_dev()))
+    assert ogcn.max_rel(out.cpu(), out_ref) <= 1e-5
+    assert ogcn.max_rel(gates[0].cpu(), gates_ref[0]) <= 1e-5 and ogcn.max_rel(gates[1].cpu(), gates_ref[1]) <= 1e-5
+    support = dense != 0
+    assert ogcn.max_rel(a.grad.cpu()[support], a_ref.grad[support]) <= 2e-5
+    assert float(a.grad.cpu()[~support].abs().max()) == 0.0              # gradient on the support only (|adj * adj.grad|)
+    sal = (a * a.grad).abs().cpu()
+    assert ogcn.max_rel(sal, (a_ref * a_ref.grad).abs().detach()) <= 2e-5
+    for k, p in om.named_parameters():
+        assert ogcn.max_rel(dict(m.named_parameters())[k].grad.cpu(), p.grad) <= 5e-5, k
+    # ---- asymmetric re-normalised sparse tensor, forward only (eval mode)
+    om.eval()
+    m.eval()
+    idx = torch.nonzero(dense).t()
+    sp = torch.sparse_coo_tensor(idx, dense[idx[0], idx[1]], dense.shape)
+    with torch.no_grad():
+        _, o_ref, _, _ = om(x.double(), sp.double(), None)
+        _, o, _, _ = m(x.to(_dev()), sp.to(_dev()), None)
+    assert ogcn.max_rel(o.cpu(), o_ref) <= 1e-5
