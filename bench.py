@@ -2,7 +2,7 @@
 """bench.py -- ChromeGCN chromosome-model hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload wg|c1|st] [--d 128|512] [--variant base|layers3|gateoff|normnone|hic1000000|hic125000]
+                    [--workload wg|c1|st] [--d-model 128|512] [--variant base|layers3|gateoff|normnone|hic1000000|hic125000]
                     [--rounds R]
 
 Metric (BASELINE.json): "GCN train step edges/sec (GE/s)".  A step is one pass of the hot path over the workload: for
@@ -59,7 +59,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="wg", choices=["wg", "c1", "st"])
-    ap.add_argument("--d", type=int, default=128, choices=[128, 256, 512])
+    # --d-model is the spelling to use under `python -m torch.distributed.run` (its own parser claims the prefix `--d`)
+    ap.add_argument("--d", "--d-model", dest="d", type=int, default=128, choices=[128, 256, 512])
     ap.add_argument("--variant", default="base", choices=VARIANTS)
     ap.add_argument("--rounds", type=int, default=0, help="optimiser steps per pass at N > 1 (0 = default schedule)")
     ap.add_argument("--st-rows", type=int, default=ST_ROWS)
