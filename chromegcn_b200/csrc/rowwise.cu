@@ -691,8 +691,8 @@ __global__ void dropout_mask_kernel(float4* mask, int64_t total4, DropoutCfg cfg
     mask[i] = cfg.enabled ? dropout_mult4(cfg, static_cast<uint64_t>(i)) : make_float4(1.f, 1.f, 1.f, 1.f);
 }
 
-// Read-bandwidth probe (tools/l2_bw.py): every CTA streams the whole buffer `reps` times with 8 independent 128-bit
-// loads in flight per thread.  A buffer that fits L2 (<= 64 MB) measures the L2 -> SM read rate the gather kernels
+// Read-bandwidth probe (tools/l2_bw.py): the grid strides over the buffer `reps` times (each element is read once per
+// repetition, by one thread) with 8 independent 128-bit loads in flight per thread.  A buffer that fits L2 (<= 64 MB) measures the L2 -> SM read rate the gather kernels
 // can hope for; a buffer of several GB measures the HBM read rate.
 __global__ void __launch_bounds__(256) membw_read_kernel(const float4* __restrict__ p, size_t n4, int reps, float* sink) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
