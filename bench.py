@@ -62,6 +62,10 @@ def parse_args():
     # --d-model is the spelling to use under `python -m torch.distributed.run` (its own parser claims the prefix `--d`)
     ap.add_argument("--d", "--d-model", dest="d", type=int, default=128, choices=[128, 256, 512])
     ap.add_argument("--variant", default="base", choices=VARIANTS)
+    ap.add_argument("--graph", default="synthetic", choices=["synthetic", "longrange", "permuted"],
+                    help="locality sensitivity of the wg / c1 workloads: longrange = contact distances log-uniform over the "
+                         "whole chromosome instead of <= 2000 bins; permuted = the synthetic graph with its windows "
+                         "relabelled at random (same degrees, no locality at all)")
     ap.add_argument("--rounds", type=int, default=0, help="optimiser steps per pass at N > 1 (0 = default schedule)")
     ap.add_argument("--st-rows", type=int, default=ST_ROWS)
     ap.add_argument("--st-pairs", type=int, default=ST_PAIRS)
@@ -87,6 +91,19 @@ def workload_chroms(name):
     return ["chr22"] if name == "c1" else list(synthetic.WHOLE_GENOME)
 
 
+def permute_pattern(indptr, indices, seed):
+    """P A P^T of a CSR pattern for a random relabelling P of the windows: degrees and entry count unchanged, every
+    neighbour row a random one (the worst case for the gather kernels' cache reuse)."""
+    import numpy as np
+    from scipy import sparse
+    n = indptr.shape[0] - 1
+    a = sparse.csr_matrix((np.ones(indices.shape[0], dtype=np.float32), indices, indptr), shape=(n, n))
+    p = np.random.default_rng(seed).permutation(n)
+    a = a[p][:, p].tocsr()
+    a.sort_indices()
+    return a.indptr.astype(np.int32), a.indices.astype(np.int32)
+
+
 def workload_name(args):
     if args.workload == "st":
         return ("ST: one synthetic chromosome, N=%d windows, %d undirected pairs (~%d M stored entries), d_model %d, "
@@ -94,15 +111,20 @@ def workload_name(args):
     base = ("C1: one chr22-sized graph (N=20000)" if args.workload == "c1" else
             "WG: whole-genome synthetic GM12878-shaped, 23 chromosome graphs (sum N ~1.18M)")
     _, _, _, hic, use_norm = variant_cfg(args)
-    return "%s, hicsize %d, hicnorm %s, variant %s" % (base, hic, "SQRTVC" if use_norm else "'' (none)", args.variant)
+    graph = {"synthetic": "", "longrange": ", contact distances log-uniform over the whole chromosome",
+             "permuted": ", windows relabelled at random (no locality)"}[args.graph]
+    return "%s, hicsize %d, hicnorm %s, variant %s%s" % (base, hic, "SQRTVC" if use_norm else "'' (none)", args.variant, graph)
 
 
-def build_inputs(chrom, hic_edges, use_norm):
+def build_inputs(chrom, hic_edges, use_norm, longrange=False):
     """Synthetic Hi-C inputs of one chromosome in the form the adjacency build takes.  hicnorm '' mode (--norm ''): no
     norm vector and the contact list pre-sorted by value, descending (data/extras/sort_hic.py:36-38; ties in file order)."""
     import numpy as np
     from chromegcn_b200 import synthetic
-    h = synthetic.make_hic(chrom, hic_edges=hic_edges)
+    if longrange:
+        h = synthetic.make_hic(chrom, hic_edges=hic_edges, max_dist_bins=synthetic.HG19_LENGTHS[chrom] // synthetic.BIN_BP - 1)
+    else:
+        h = synthetic.make_hic(chrom, hic_edges=hic_edges)
     if use_norm:
         return h.window_starts, h.bin1, h.bin2, h.val, h.norm
     order = np.argsort(-h.val, kind="stable")
@@ -401,8 +423,10 @@ def run_chromosomes(args, torch, dist, dev, world, rank, sampler):
     graphs, feats_host, panels, targets, probs = {}, {}, {}, {}, {}
     local_edges = 0
     for c in mine:
-        w, b1, b2, v, nv = build_inputs(c, hic, use_norm)
+        w, b1, b2, v, nv = build_inputs(c, hic, use_norm, args.graph == "longrange")
         ip, ix = ops.adjacency_build(w, b1, b2, v, nv, 1, hic, dev)          # the product's own build (cgcn_adj_build)
+        if args.graph == "permuted":
+            ip, ix = permute_pattern(ip, ix, 4000 + synthetic.chrom_index(c))
         graphs[c] = HiCGraph.from_csr_pattern(ip, ix, dev, name=c)
         n = graphs[c].n
         f = synthetic.make_features(c, n, D, NCLASS)
@@ -491,7 +515,7 @@ def run_chromosomes(args, torch, dist, dev, world, rank, sampler):
             traceback.print_exc()
             roofline = {"bound": "hbm", "error": "%s: %s" % (type(exc).__name__, exc)}
     config = {"workload": workload_name(args), "d_model": D, "gcn_layers": layers, "nclass": NCLASS, "gate": gate, "adj_type": "hic",
-              "hicnorm": "SQRTVC" if use_norm else "", "hicsize": hic, "variant": args.variant, "optim": "sgd", "gcn_dropout": DROPOUT,
+              "hicnorm": "SQRTVC" if use_norm else "", "hicsize": hic, "variant": args.variant, "graph": args.graph, "optim": "sgd", "gcn_dropout": DROPOUT,
               "strands": 2, "total_stored_entries": total_edges,
               "parallelism": "chromosome-sharded x%d, %d lock-step round(s) per pass (balanced packing, gradient accumulation inside "
                              "a rank's cell), one flat-gradient allreduce + optimiser step per round" % (world, len(schedule)),
