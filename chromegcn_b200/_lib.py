@@ -11,7 +11,7 @@ from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libchromegcn.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_LAYERS = 4
 MAX_PEERS = 8
 
@@ -101,6 +101,11 @@ PROTOTYPES = {
     "cgcn_train_step_bits": (C.c_int, [C.POINTER(Model), _P, _P, _P, _P]),
     "cgcn_sgd_step": (C.c_int, [_P, _P, _P, _I64, _F32, _F32, _F32, _F32, _P]),
     "cgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _I64, _F32, _P]),
+    "cgcn_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "cgcn_comm_init": (C.c_int, [C.POINTER(_P), C.c_char_p, _I32, _I32]),
+    "cgcn_comm_destroy": (C.c_int, [_P]),
+    "cgcn_comm_allreduce_sum": (C.c_int, [_P, _P, _SZ, _P]),
+    "cgcn_comm_allgather": (C.c_int, [_P, _P, _P, _SZ, _P]),
     "cgcn_membw_read": (C.c_int, [_P, _SZ, _I32, _P, _P]),
     "cgcn_interleave_strands": (C.c_int, [C.POINTER(_P), _I32, _I32, _I32, _P, _P]),
     "cgcn_deinterleave_strands": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_P), _P]),

@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libchromegcn.so")
-SOURCES = ["spmm.cu", "fused_layer.cu", "gemm_ffma.cu", "gemm_tc.cu", "rowwise.cu", "adjacency.cu", "metrics.cu", "ingest.cu", "model.cu"]
+SOURCES = ["spmm.cu", "fused_layer.cu", "gemm_ffma.cu", "gemm_tc.cu", "rowwise.cu", "adjacency.cu", "metrics.cu", "ingest.cu", "comm.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-pthread", "--expt-relaxed-constexpr", "-cudart", "static"]
 
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-fPIC",
-            "-o", LIB_PATH, *objs]
+            "-o", LIB_PATH, *objs, "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -54,6 +54,51 @@ def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> None:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
 
 
+class NativeComm:
+    """The library's own NCCL communicator (`cgcn_comm_*`, include/chromegcn.h): the calls a host without Python makes
+    for the exchanges above.  Here it is exercised next to torch.distributed (tests/test_gpu_sharded.py), not used
+    by default: `id_bytes` comes from `NativeComm.unique_id()` on rank 0 and reaches the other ranks by any channel
+    (the tests broadcast it with torch.distributed)."""
+
+    def __init__(self, id_bytes: bytes, world: int, rank: int, device=None):
+        import ctypes as C
+        from . import _lib
+        self._lib = _lib
+        self._h = C.c_void_p()
+        self.world, self.rank = int(world), int(rank)
+        self.device = _lib.require_cuda(device)
+        assert len(id_bytes) == 128
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().cgcn_comm_init(C.byref(self._h), bytes(id_bytes), self.world, self.rank), "cgcn_comm_init")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _lib
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().cgcn_comm_unique_id(buf), "cgcn_comm_unique_id")
+        return buf.raw
+
+    def allreduce_sum(self, t: torch.Tensor) -> None:
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.load().cgcn_comm_allreduce_sum(self._h, t.data_ptr(), t.numel(), self._lib.current_stream()),
+                            "cgcn_comm_allreduce_sum")
+
+    def allgather(self, send: torch.Tensor, recv: torch.Tensor) -> None:
+        nbytes = send.numel() * send.element_size()
+        assert send.is_cuda and recv.is_cuda and send.is_contiguous() and recv.is_contiguous()
+        assert recv.numel() * recv.element_size() == nbytes * self.world
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.load().cgcn_comm_allgather(self._h, send.data_ptr(), recv.data_ptr(), nbytes,
+                                                                 self._lib.current_stream()), "cgcn_comm_allgather")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.check(self._lib.load().cgcn_comm_destroy(self._h), "cgcn_comm_destroy")
+            self._h = None
+
+
 def default_rounds(n_items: int, world: int) -> int:
     """Optimiser steps per pass over the chromosomes: one per chromosome on one rank (the reference,
     finetune.py:39-49); ONE on several ranks: every rank walks its LPT share of the chromosomes accumulating

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CGCN_ABI_VERSION 7
+#define CGCN_ABI_VERSION 8
 #define CGCN_MAX_LAYERS 4
 #define CGCN_MAX_PEERS 8    /* GPUs of one NVSwitch box */
 
@@ -398,6 +398,28 @@ int cgcn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_
 int cgcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
                    float lr, float beta1, float beta2, float eps, int64_t step_index, float grad_scale,
                    cgcn_stream_t stream);
+
+/* ------------------------------------------ collectives for a non-Python host ---- */
+/* The multi-GPU paths need three exchanges and nothing else: the flat-gradient sum of the chromosome-sharded pass
+ * (the reference has ONE model and steps it once per chromosome, finetune.py:46-49; N replicas must sum their
+ * gradients before the shared step), the BatchNorm column sums of the row-partitioned graph (models/ChromeModels.py:49
+ * normalises over ALL windows of the chromosome), and -- only for the copy-based exchange -- the all-gather of a
+ * panel's row blocks.  The Python host uses torch.distributed for them (chromegcn_b200/dist.py); these entry points
+ * give a C / C++ / Go host the same three calls over NCCL without any Python.  NCCL is loaded at first use with
+ * dlopen("libnccl.so.2") (the copy already mapped into the process if there is one): the library itself carries no
+ * link-time NCCL dependency, and every call returns CGCN_ERR_INVALID with a message when NCCL cannot be loaded.
+ * One communicator per process, bound to the device that is current at cgcn_comm_init. */
+typedef struct cgcn_comm* cgcn_comm_t;
+#define CGCN_COMM_ID_BYTES 128
+/* rank 0: fill 128 bytes; the host ships them to the other ranks by its own means (file, socket, MPI) */
+int cgcn_comm_unique_id(unsigned char id_host[CGCN_COMM_ID_BYTES]);
+/* collective over all ranks of the job */
+int cgcn_comm_init(cgcn_comm_t* comm_host, const unsigned char id_host[CGCN_COMM_ID_BYTES], int32_t world, int32_t rank);
+int cgcn_comm_destroy(cgcn_comm_t comm);
+/* buf (device, fp32) <- sum over ranks, in place; enqueued on `stream` */
+int cgcn_comm_allreduce_sum(cgcn_comm_t comm, float* buf, size_t count, cgcn_stream_t stream);
+/* recv[r * bytes_per_rank ...] <- rank r's `send` (device buffers; recv holds world * bytes_per_rank bytes) */
+int cgcn_comm_allgather(cgcn_comm_t comm, const void* send, void* recv, size_t bytes_per_rank, cgcn_stream_t stream);
 
 /* --------------------------------------------------------------- utilities ---- */
 /* Read-bandwidth probe (measurement aid, tools/l2_bw.py): streams `bytes` of `buf` `reps` times with L2-only loads.  A

@@ -62,7 +62,26 @@ def _worker(rank, world, port, ret):
         cdist.sharded_train_epoch(ChromosomeEngine(m, 2), FlatSGD(m, lr=0.25), schedule, rank, graphs, panels, targets, probs, losses)
         torch.cuda.synchronize(dev)
         # numpy arrays pickle by value (tensors would travel as shared-memory handles through the manager process)
-        ret[rank] = {"schedule": schedule, "params": {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}}
+        out = {"schedule": schedule, "params": {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}}
+        # the library's own NCCL entry points (cgcn_comm_*, what a host without Python calls) against torch.distributed
+        box = [cdist.NativeComm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, 0)
+        comm = cdist.NativeComm(box[0], world, rank, dev)
+        g = torch.Generator(device=dev).manual_seed(11 + rank)
+        t = torch.randn(46825, device=dev, generator=g)
+        mine_t, theirs = t.clone(), t.clone()
+        comm.allreduce_sum(mine_t)
+        dist.all_reduce(theirs)
+        part = torch.randn(300, 256, device=dev, generator=g)
+        got = torch.empty(world * 300, 256, device=dev)
+        want_parts = [torch.empty_like(part) for _ in range(world)]
+        comm.allgather(part, got)
+        dist.all_gather(want_parts, part)
+        torch.cuda.synchronize(dev)
+        out["native_allreduce_equal"] = bool(torch.equal(mine_t, theirs))
+        out["native_allgather_equal"] = bool(torch.equal(got, torch.cat(want_parts)))
+        comm.close()
+        ret[rank] = out
     finally:
         dist.destroy_process_group()
 
@@ -84,6 +103,8 @@ def test_chromosome_sharded_pass_two_gpus_matches_mean_gradient_oracle():
         assert p.exitcode == 0
     a, b = ret[0], ret[1]
     assert a["schedule"] == b["schedule"]
+    for r in (a, b):
+        assert r["native_allreduce_equal"] and r["native_allgather_equal"]
     for k in a["params"]:
         # replicas stay bit-identical, BatchNorm buffers included: sharded_train_epoch ends with
         # sync_batchnorm_buffers (rank average of running_mean / running_var, summed num_batches_tracked), so an eval
@@ -115,3 +136,19 @@ def test_chromosome_sharded_pass_two_gpus_matches_mean_gradient_oracle():
         if "num_batches" in k or "running" in k:
             continue
         assert ogcn.max_rel(torch.from_numpy(v), want[k]) <= 2e-5, k
+
+
+def test_native_comm_world_one_is_the_identity():
+    """cgcn_comm_* on a single rank (the driver's one-GPU lease): NCCL loads, the communicator initialises, the
+    sum over one rank and the gather of one block leave the data as it was."""
+    from chromegcn_b200 import dist as cdist
+    dev = torch.device("cuda", 0)
+    comm = cdist.NativeComm(cdist.NativeComm.unique_id(), 1, 0, dev)
+    t = torch.randn(1000, device=dev)
+    u = t.clone()
+    comm.allreduce_sum(u)
+    got = torch.empty_like(t)
+    comm.allgather(t, got)
+    torch.cuda.synchronize(dev)
+    assert torch.equal(u, t) and torch.equal(got, t)
+    comm.close()

@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_abi_version_and_struct_layout(lib):
     import ctypes as C
     from chromegcn_b200 import _lib
-    assert lib.cgcn_abi_version() == _lib.ABI_VERSION == 7
+    assert lib.cgcn_abi_version() == _lib.ABI_VERSION == 8
     assert lib.cgcn_sizeof(0) == C.sizeof(_lib.Graph)
     assert lib.cgcn_sizeof(1) == C.sizeof(_lib.Params)
     assert lib.cgcn_sizeof(2) == C.sizeof(_lib.Model)
@@ -113,3 +113,18 @@ def test_pack_targets_bit_layout():
             assert not (w[:, -1] >> np.uint32(c % 32)).any()       # padding bits stay clear
     t[0, 0] = 0.25
     assert ops.pack_targets(torch.from_numpy(t)) is None
+
+
+def test_comm_entry_points_validate_arguments_without_a_gpu():
+    """cgcn_comm_* (collectives for a non-Python host): argument errors are reported before NCCL is touched."""
+    import ctypes as C
+    from chromegcn_b200 import _lib
+    lib = _lib.load()
+    handle = C.c_void_p()
+    ident = C.create_string_buffer(128)
+    assert lib.cgcn_comm_init(C.byref(handle), ident, 2, 5) == -1
+    assert b"rank 5 of world 2" in lib.cgcn_last_error()
+    assert lib.cgcn_comm_init(None, ident, 1, 0) == -1
+    assert lib.cgcn_comm_allreduce_sum(None, None, 4, None) == -1
+    assert lib.cgcn_comm_allgather(None, None, None, 4, None) == -1
+    assert lib.cgcn_comm_destroy(None) == 0
