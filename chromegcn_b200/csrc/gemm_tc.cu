@@ -355,6 +355,8 @@ constexpr int GR_OP_BYTES = 2 * CHUNK_BYTES;                     // one operand,
 constexpr int GR_STAGE_BYTES = 2 * GR_OP_BYTES;                  // A + B: 64 KB
 constexpr int GR_SMEM = STAGES * GR_STAGE_BYTES + STG_BYTES + 256 + 1024;
 
+// GR_SLOTS: register look-ahead of the producers, in 32-row chunks
+template <int GR_SLOTS>
 __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -393,8 +395,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcAr
     // (c/8)*4096 + r*128 + ((((c%8)/2) ^ (r%4)) * 32) + (c%2)*16      [LBO = 4096, SBO = 512].
     const int pt = threadIdx.x - (MMA_WARP + 1) * 32;
     uint32_t stage = 0, phase = 0;
-    // two chunks of look-ahead in registers (2 x 8 float4 per thread = 64 KB in flight per SM)
-    float4 va[2][4], vb[2][4];
+    // GR_SLOTS chunks of look-ahead in registers (8 float4 per thread and chunk: 32 KB per chunk in flight per SM)
+    float4 va[GR_SLOTS][4], vb[GR_SLOTS][4];
     auto issue = [&](int ch, int slot) {
       const int64_t row0 = r_begin + static_cast<int64_t>(ch) * KCH;
 #pragma unroll
@@ -407,11 +409,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcAr
         vb[slot][i] = (ok && c * 4 < p.nb_valid) ? ldg4(p.B + grow * p.ldb + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    issue(0, 0);
-    issue(1, 1);
-    for (int ch0 = 0; ch0 < chunks; ch0 += 2) {
 #pragma unroll
-      for (int slot = 0; slot < 2; ++slot) {
+    for (int slot = 0; slot < GR_SLOTS; ++slot) issue(slot, slot);
+    for (int ch0 = 0; ch0 < chunks; ch0 += GR_SLOTS) {
+#pragma unroll
+      for (int slot = 0; slot < GR_SLOTS; ++slot) {
         const int ch = ch0 + slot;
         if (ch >= chunks) break;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_gram_tc_kernel(const GramTcAr
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-        issue(ch + 2, slot);
+        issue(ch + GR_SLOTS, slot);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -590,9 +592,11 @@ int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float
     set_error("cgcn_gemm_gram(tcgen05): workspace %zu < %zu bytes", workspace_bytes, gram_workspace_bytes(m));
     return CGCN_ERR_WORKSPACE;
   }
+  static const int slots = getenv("CGCN_GRAM_SLOTS") ? atoi(getenv("CGCN_GRAM_SLOTS")) : 2;   // developer aid: 3 chunks of look-ahead measured no faster (15.85 vs 15.79 ms per pass)
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
-    CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GR_SMEM));
+    CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_gram_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GR_SMEM));
+    CGCN_CUDA(cudaFuncSetAttribute(tc::gemm_gram_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GR_SMEM));
   }
   // one CTA per SM (the kernel owns the whole shared memory): a single wave, <= #SM partial tiles
   int64_t rows = (m + sm_count() - 1) / sm_count();
@@ -600,7 +604,10 @@ int gemm_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float
   rows = (rows + tc::KCH - 1) / tc::KCH * tc::KCH;
   const int parts = static_cast<int>((m + rows - 1) / rows);
   tc::GramTcArgs p{A, lda, B, ldb, m, rows, static_cast<float*>(workspace), ka, nb};
-  CGCN_CUDA(launch_k(tc::gemm_gram_tc_kernel, dim3(parts), dim3(tc::THREADS), tc::GR_SMEM, stream, p));
+  if (slots == 2)
+    CGCN_CUDA(launch_k(tc::gemm_gram_tc_kernel<2>, dim3(parts), dim3(tc::THREADS), tc::GR_SMEM, stream, p));
+  else
+    CGCN_CUDA(launch_k(tc::gemm_gram_tc_kernel<3>, dim3(parts), dim3(tc::THREADS), tc::GR_SMEM, stream, p));
   CGCN_TRY(check_launch("gemm_gram_tc_kernel"));
   gram_finalize_launch(p.partial, parts, tc::TILE * tc::TILE, tc::TILE, ka, nb, C, ldc, accumulate, stream);
   return check_launch("gram_finalize_kernel");
