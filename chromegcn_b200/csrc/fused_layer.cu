@@ -171,12 +171,15 @@ __global__ void __launch_bounds__(threads_for(G_WARPS, E), 1) fused_layer_kernel
     }
     tmem_wait_st();
     tc_fence_before();
-    named_bar_sync(3, 5 * 32);
-    tc_fence_after();
+    if constexpr (E != 8) {                        // E == 8: after these warps have given registers back (see below)
+      named_bar_sync(3, 5 * 32);
+      tc_fence_after();
+    }
   }
 
   if (warp >= EPI_WARPS) {
     // =========================================================== gather warps
+    if constexpr (E == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // Each warp owns RPW window rows of every tile and walks their neighbour lists as ONE stream of "segments" (<= 32
     // column indices of one row, held one per lane) cut into batches of U neighbours.  Two register sets alternate:
     // while batch i is being summed, batch i+1 -- of the same segment, or the first of the next row / tile -- is already
@@ -428,6 +431,18 @@ __global__ void __launch_bounds__(threads_for(G_WARPS, E), 1) fused_layer_kernel
     }
   } else {
     // =========================================================== epilogue warps
+    if constexpr (E == 8) {
+      // 24 warps start at 80 registers; the epilogue warps drop to 64 so that the 16 gather warps can grow to 88.
+      // setmaxnreg.inc draws only on what warps of this CTA have released (SASS: USETMAXREG.TRY_ALLOC.CTAPOOL), not on
+      // registers the launch left unallocated: 8 x 16 released = 16 x 8 acquired; asking for more (56 / 96, 64 / 96)
+      // spins forever.  The weight-image warps release theirs BEFORE they wait for the issuing warp on barrier 3: that
+      // warp may itself be waiting for these registers.
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      if (warp < 4 && ntile > 0) {
+        named_bar_sync(3, 5 * 32);
+        tc_fence_after();
+      }
+    }
     // Phase A (thread = output feature: the accumulator is y^T, TMEM lane f = feature f, column r = tile row r):
     // TMEM -> + bias -> row-major shared y tile (one conflict-free 128-byte store per row per warp).
     // Phase B (LPR lanes per row, RPI rows per warp step; lane q owns the float4 column groups cc * CSTRIDE + 4 q):
