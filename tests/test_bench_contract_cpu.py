@@ -19,7 +19,8 @@ def _line(path):
 
 
 @pytest.mark.parametrize("name,n_gpus", [("r01b_bench_wg.json", 1), ("r01b_bench_wg_2gpu.json", 2), ("r01b_bench_wg_8gpu.json", 8),
-                                         ("r01b_bench_c1.json", 1)])
+                                         ("r01b_bench_c1.json", 1), ("r02_bench_wg_1gpu.json", 1), ("r02_bench_wg_4gpu.json", 4),
+                                         ("r02_bench_wg_8gpu.json", 8), ("r02_bench_c1_1gpu.json", 1)])
 def test_committed_bench_lines_follow_the_contract(name, n_gpus):
     d = _line(os.path.join(ROOT, "profiles", name))
     assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
@@ -42,6 +43,29 @@ def test_committed_bench_lines_follow_the_contract(name, n_gpus):
         assert r["traffic"] and r["traffic"] < r["algorithmic_bytes_per_launch"]      # no wasted re-reads
         b = d["cpu_baseline"]
         assert {"value", "unit", "cores", "kind", "sample"} <= set(b) and b["kind"] in ("port", "reference") and b["cores"] >= 1
+    if name.startswith("r02") and n_gpus == 1 and "WG" in d["config"]["workload"]:
+        # round 2: the cache-served algorithmic fraction is reported next to the honest ones
+        assert 0 < r["compulsory_frac"] < 1 and 0 < r["time_bound_frac"] <= 1 and r["l2_read_peak"] > r["peak"]
+        assert 0 < r["spmm"]["time_bound_frac"] <= 1
+        g = d["gpu_baseline"]
+        assert g["kind"] == "port" and 0 < g["e2e"] < g["value"] < d["value"]
+
+
+def test_permuted_graph_keeps_degrees_and_symmetry():
+    """bench.py --graph permuted: P A P^T of a symmetric pattern (the locality sensitivity line)."""
+    import numpy as np
+    from scipy import sparse
+    sys.path.insert(0, ROOT)
+    import bench
+    a = sparse.random(300, 300, 0.03, format="csr", random_state=3)
+    a = ((a + a.T) > 0).astype(np.float32).tocsr()
+    a.sort_indices()
+    ip, ix = bench.permute_pattern(a.indptr.astype(np.int32), a.indices.astype(np.int32), 9)
+    b = sparse.csr_matrix((np.ones(ix.shape[0]), ix, ip), shape=a.shape)
+    assert ix.shape[0] == a.nnz and (b != b.T).nnz == 0
+    assert sorted(np.diff(ip).tolist()) == sorted(np.diff(a.indptr).tolist())
+    assert all(np.all(np.diff(ix[ip[i]:ip[i + 1]]) > 0) for i in range(300))          # rows column-sorted
+    assert not np.array_equal(ix, a.indices)
 
 
 def test_reference_arm_runs_on_the_host_and_prints_one_line():
