@@ -128,3 +128,48 @@ def test_comm_entry_points_validate_arguments_without_a_gpu():
     assert lib.cgcn_comm_allreduce_sum(None, None, 4, None) == -1
     assert lib.cgcn_comm_allgather(None, None, None, 4, None) == -1
     assert lib.cgcn_comm_destroy(None) == 0
+
+
+def _header_prototypes():
+    """name -> list of parameter declarations, parsed from include/chromegcn.h."""
+    hdr = open(os.path.join(REPO, "include", "chromegcn.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|int64_t|size_t|const char\s*\*)\s+(cgcn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        params = " ".join(m.group(2).split())
+        protos[m.group(1)] = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+    return protos
+
+
+def test_ctypes_prototypes_agree_with_the_header():
+    """Every binding in _lib.PROTOTYPES has the header's parameter count, and each parameter's ctypes class matches the
+    C declaration's class (pointer / 32-bit / 64-bit / float): a drifted binding would corrupt the call frame silently."""
+    import ctypes as C
+    from chromegcn_b200 import _lib
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib.PROTOTYPES)
+
+    def c_class(decl):
+        if "*" in decl or "[" in decl or re.search(r"\bcgcn_(stream|comm)_t\b", decl):
+            return "ptr"
+        if re.search(r"\b(int64_t|uint64_t|size_t)\b", decl):
+            return "i64"
+        if re.search(r"\b(float)\b", decl):
+            return "f32"
+        if re.search(r"\b(double)\b", decl):
+            return "f64"
+        if re.search(r"\b(int32_t|uint32_t|int)\b", decl):
+            return "i32"
+        raise AssertionError("unclassified parameter: %r" % decl)
+
+    def py_class(t):
+        if t in (C.c_void_p, C.c_char_p) or isinstance(t, type(C.POINTER(C.c_int))):
+            return "ptr"
+        return {C.c_int64: "i64", C.c_uint64: "i64", C.c_size_t: "i64", C.c_float: "f32", C.c_double: "f64",
+                C.c_int32: "i32", C.c_uint32: "i32", C.c_int: "i32"}[t]
+
+    for name, params in sorted(protos.items()):
+        _, argtypes = _lib.PROTOTYPES[name]
+        assert len(argtypes) == len(params), (name, len(argtypes), params)
+        for t, decl in zip(argtypes, params):
+            assert py_class(t) == c_class(decl), (name, decl, t)
