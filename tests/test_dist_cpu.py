@@ -91,6 +91,25 @@ def _worker(rank, world, port, ret):
         local = torch.stack([got[lc[lp[i]: lp[i + 1]]].mean(0) for i in range(e - b)])
         want = torch.stack([full[ci[rp[i]: rp[i + 1]]].mean(0) for i in range(b, e)])
         assert torch.allclose(local, want)
+        # (3) BatchNorm buffers after a sharded pass: rank average of the running statistics, num_batches_tracked =
+        #     start + the calls of ALL ranks (what one model walking every chromosome would count)
+        holder = type("M", (), {})()
+        holder.batch_norm = torch.nn.BatchNorm1d(4)
+        bn = holder.batch_norm
+        before = bn.num_batches_tracked.clone()
+        bn.running_mean.fill_(float(rank + 1))
+        bn.running_var.fill_(float(10 * (rank + 1)))
+        bn.num_batches_tracked.add_(3 + rank)                     # rank 0 saw 3 strand calls, rank 1 saw 4
+        cdist.sync_batchnorm_buffers(holder, None, before)
+        assert torch.equal(bn.running_mean, torch.full((4,), 1.5)) and torch.equal(bn.running_var, torch.full((4,), 15.0))
+        assert int(bn.num_batches_tracked) == 7
+        # (4) one optimiser step on the MEAN of a round's summed gradients with a stock torch optimiser (no grad_scale
+        #     attribute): the buffer is scaled in place, nothing persists on the optimiser
+        p = torch.nn.Parameter(torch.ones(5))
+        p.grad = torch.full((5,), 4.0)
+        opt = torch.optim.SGD([p], lr=0.5)
+        cdist.step_on_mean(opt, p.grad, 0.25)
+        assert torch.allclose(p.detach(), torch.full((5,), 0.5)) and not hasattr(opt, "grad_scale")
         ret[rank] = 1
     finally:
         dist.destroy_process_group()
